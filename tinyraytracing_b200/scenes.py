@@ -1,0 +1,115 @@
+"""Scene fixtures: write the packed example-scenes-cg22 inputs back out as OBJ / MTL / XML files.
+
+The reference takes its inputs as files (stdin protocol, main.cpp:46-55; loaders scene.cpp:3-213) and so
+does this framework's C++ host (csrc/host/scene.cpp).  /root/reference is not available on the GPU box, so
+`scenes/<name>.npz` (made by tools/pack_scenes.py) carries the parsed content and this module regenerates
+equivalent text files: same statement order (so the `isvnvt` slot-order quirk of scene.cpp:149-153 is
+preserved), numbers printed with %.9g so every float32 round-trips exactly.
+
+Textures: the reference decodes JPEG with cv::imread (material.cpp:6).  There is no JPEG decoder on the
+C++ side here; `materialize` pre-decodes with Python cv2 (the same OpenCV decoder family, BGR order) into
+the side-car `<texture>.bgr` ("BGR8", int32 rows, int32 cols, bytes) that Material::readinMap reads.
+"""
+import json
+import os
+import zlib
+
+import numpy as np
+
+SCENE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "scenes")
+NAMES = ("back", "veach-mis", "staircase")
+
+
+def _g(x):
+    return "%.9g" % float(x)
+
+
+def write_bgr_sidecar(path, img):
+    """img: HxWx3 uint8 BGR (cv2.imread layout) -> `path` side-car understood by Material::readinMap."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    with open(path, "wb") as f:
+        f.write(b"BGR8")
+        f.write(np.array([img.shape[0], img.shape[1]], np.int32).tobytes())
+        f.write(img.tobytes())
+
+
+def materialize(name, outdir, width=None, height=None):
+    """Write <outdir>/<stem>.{obj,mtl,xml} (+ textures) for packed scene `name`.
+
+    width/height override the XML resolution (the reference takes resolution from the XML, scene.cpp:13-14).
+    Returns dict(basedir, obj, mtl, xml, width, height).
+    """
+    z = np.load(os.path.join(SCENE_DIR, name + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    stem = meta["stem"]
+    os.makedirs(outdir, exist_ok=True)
+    v, vn, vt, faces, fmtl = z["v"], z["vn"], z["vt"], z["faces"], z["face_mtl"]
+
+    with open(os.path.join(outdir, stem + ".obj"), "w") as f:
+        f.write("# regenerated from scenes/%s.npz (%s)\n" % (name, meta["source"]))
+        for p in v:
+            f.write("v %s %s %s\n" % (_g(p[0]), _g(p[1]), _g(p[2])))
+
+        def emit_vt():
+            for p in vt:
+                f.write("vt %s %s\n" % (_g(p[0]), _g(p[1])))
+
+        def emit_vn():
+            for p in vn:
+                f.write("vn %s %s %s\n" % (_g(p[0]), _g(p[1]), _g(p[2])))
+
+        # scene.cpp:149-153: slots are read v/vn/vt unless a vt line is seen before any vn line
+        if meta["isvnvt"]:
+            emit_vn(), emit_vt()
+        else:
+            emit_vt(), emit_vn()
+        cur = None
+        names = meta["obj_mtl_names"]
+        for tri, m in zip(faces, fmtl):
+            if m != cur:
+                cur = m
+                if names[m] != "":
+                    f.write("usemtl %s\n" % names[m])
+            f.write("f %d/%d/%d %d/%d/%d %d/%d/%d\n" % tuple(int(x) for x in tri.reshape(-1)))
+
+    with open(os.path.join(outdir, stem + ".mtl"), "w") as f:
+        for tok in meta["mtl"]:
+            f.write(" ".join(tok) + "\n")
+
+    xml = meta["xml"]
+    cam = dict(xml["camera"])
+    if width is not None:
+        cam["width"] = str(int(width))
+    if height is not None:
+        cam["height"] = str(int(height))
+
+    def attrs(d):
+        return " ".join('%s="%s"' % kv for kv in d.items())
+
+    with open(os.path.join(outdir, stem + ".xml"), "w") as f:
+        f.write('<?xml version="1.0" encoding="utf-8"?>\n<camera %s>\n' % attrs(cam))
+        for tag in ("eye", "lookat", "up"):
+            f.write("\t<%s %s/>\n" % (tag, attrs(xml[tag])))
+        f.write("</camera>\n")
+        for l in xml["lights"]:
+            f.write("<light %s/>\n" % attrs(l))
+
+    for rel, info in meta["textures"].items():
+        import cv2
+
+        p = os.path.join(outdir, rel)
+        os.makedirs(os.path.dirname(p), exist_ok=True)
+        raw = z["jpeg:" + rel]
+        raw.tofile(p)
+        img = cv2.imdecode(raw, cv2.IMREAD_COLOR)
+        if img is None or img.shape[0] != info["rows"] or img.shape[1] != info["cols"]:
+            raise RuntimeError("texture decode failed: " + rel)
+        if zlib.crc32(img.tobytes()) != info["crc32"]:
+            # a different libjpeg build may differ in low bits; parity is then statistical only
+            import warnings
+
+            warnings.warn("decoded texture %s differs from the pack-time decode (crc32)" % rel)
+        write_bgr_sidecar(p + ".bgr", img)
+
+    return dict(basedir=outdir, obj=os.path.join(outdir, stem + ".obj"), mtl=os.path.join(outdir, stem + ".mtl"),
+                xml=os.path.join(outdir, stem + ".xml"), width=int(cam["width"]), height=int(cam["height"]))

@@ -1,0 +1,187 @@
+/* trt.h — C ABI of the B200-native hot path of TinyRayTracing (libtrt_b200.so).
+ *
+ * The reference has no plugin / FFI interface: its hot path is reached by plain C++ calls
+ *   main.cpp:76      buildBVH(scene.triangles, 0, n-1, 8)
+ *   main.cpp:95-101  Camera::getRay -> traverseBVH -> shade            (bvh.h:28-32, pathtracing.h:14-17)
+ *   main.cpp:79-113  the sample / pixel loop that accumulates into `double image[W*H*3]`
+ * This header is the boundary that replaces the loop body: the host keeps the reference's Scene / Camera /
+ * Material / BVH classes and loaders (csrc/host), converts them ONCE into the POD arrays below after buildBVH,
+ * and every traversal / shading step then runs in hand-written sm_100a kernels.
+ *
+ * Conventions: every call returns 0 on success or a negative trt_status; trt_last_error() gives the text.
+ * No call exits the process, none falls back to the CPU: without an sm_100 device trt_scene_create fails.
+ * Calls on one trt_scene must be serialised by the caller (the reference's main is single-threaded outside
+ * its OpenMP loop, which this library replaces).  Plain pointers and sizes only — no C++ / torch types.
+ */
+#ifndef TRT_H
+#define TRT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRT_VERSION 100
+
+typedef enum trt_status {
+    TRT_OK = 0,
+    TRT_ERR_INVALID = -1,   /* bad argument / inconsistent description            */
+    TRT_ERR_NO_DEVICE = -2, /* no sm_100 GPU: there is deliberately no CPU path   */
+    TRT_ERR_CUDA = -3,      /* a CUDA runtime call failed (text in trt_last_error) */
+    TRT_ERR_LIMIT = -4      /* a documented capacity limit was exceeded           */
+} trt_status;
+
+/* reference INF (bvh.h:5): distance reported for a miss */
+#define TRT_INF 114514.0f
+
+/* Material record = the fields of reference `Material` (material.h:11-33) that shade()/nextRay() read. */
+typedef struct trt_material {
+    float Kd[3], Ks[3], Tr[3];
+    float Ns, Ni;
+    float radiance[3];   /* scene.cpp:52 */
+    int32_t is_emissive; /* scene.cpp:51 */
+    int32_t texture;     /* index into textures, -1 when map_Kd == "" (material.h:20) */
+    double area;         /* total light area, scene.cpp:202 */
+} trt_material;
+
+/* One <light> of the XML, in XML order (scene.cpp:23-54).  Its triangles are the reference's
+ * materials[mtl].triangles (scene.cpp:204): OBJ order, `cum_area` = running sum (scene.cpp:201-203). */
+typedef struct trt_light {
+    int32_t material;  /* index into materials */
+    int32_t first_tri; /* offset into light_v / light_vn / light_cum_area */
+    int32_t n_tris;
+    int32_t _pad;
+} trt_light;
+
+typedef struct trt_texture {
+    int32_t rows, cols;  /* cv::Mat rows / cols (material.cpp:10) */
+    const uint8_t *bgr;  /* rows*cols*3, OpenCV BGR byte order as cv::imread returns it */
+} trt_texture;
+
+/* Scene description: POD view of the reference's Scene AFTER buildBVH (post-build triangle order).
+ * Triangle identity = position in Scene::triangles after buildBVH (the reference has no id field,
+ * triangle.h:25 is commented out). */
+typedef struct trt_scene_desc {
+    int32_t n_tris;
+    const float *v;      /* n_tris*9 : v[0].xyz v[1].xyz v[2].xyz           (triangle.h:17) */
+    const float *vn;     /* n_tris*9 : vertex normals                        (triangle.h:18) */
+    const float *vt;     /* n_tris*6 : vertex uvs                            (triangle.h:19) */
+    const float *normal; /* n_tris*3 : face normal EXACTLY as scene.cpp:196 computed it     */
+    const int32_t *mtl;  /* n_tris   : material index                                         */
+
+    /* reference BVH topology, pre-order array of the pointer tree buildBVH returns (bvh.cpp:16-144) */
+    int32_t n_nodes;
+    const float *node_box;    /* n_nodes*6 : AA.xyz BB.xyz (bvh.h:21)                          */
+    const int32_t *node_link; /* n_nodes*4 : left, right (node indices, -1 = NULL), index, num */
+
+    int32_t n_materials;
+    const trt_material *materials;
+    int32_t n_lights;
+    const trt_light *lights;
+    int32_t n_light_tris;
+    const float *light_v;         /* n_light_tris*9 */
+    const float *light_vn;        /* n_light_tris*9 */
+    const double *light_cum_area; /* n_light_tris   */
+    int32_t n_textures;
+    const trt_texture *textures;
+
+    /* camera as computed by Camera::setCamera on the host (camera.cpp:3-17) */
+    float eye[3], lower_left_corner[3], horizontal[3], vertical[3];
+    int32_t width, height;
+} trt_scene_desc;
+
+typedef struct trt_scene trt_scene;
+
+/* ---- lifetime ------------------------------------------------------------------------------------ */
+
+/* Number of usable sm_100 devices (0 when none / no driver). */
+int trt_device_count(void);
+
+/* Copies the description to `device` and builds the GPU acceleration layout from the reference topology.
+ * The caller keeps ownership of every input pointer; nothing is referenced after the call returns.
+ * Replaces: nothing in the reference (there the Scene is used in place); called once after main.cpp:76. */
+int trt_scene_create(const trt_scene_desc *desc, int device, trt_scene **out);
+void trt_scene_destroy(trt_scene *scene);
+
+/* Page-locked host memory for ray / result buffers: the blocking entry points DMA straight from / to such
+ * buffers; pageable buffers are staged through internal pinned chunks (one extra host copy). */
+void *trt_host_alloc(size_t bytes);
+void trt_host_free(void *p);
+
+/* ---- closest hit: replaces traverseBVH (bvh.cpp:146-175) for a batch of rays --------------------- */
+
+#define TRT_TRACE_DEVICE_PTRS 1u /* rays / outputs are device pointers on the scene's device          */
+#define TRT_TRACE_EXHAUSTIVE 2u  /* walk the reference topology with the reference's visiting rule
+                                    (no ordering, no pruning: bvh.cpp:156-174) — validation mode     */
+#define TRT_TRACE_REFTOPO 4u     /* ordered + pruned walk of the reference binary topology          */
+
+/* rays6: n*(origin.xyz, direction.xyz) float32.  tri_id: post-build triangle index of the reference's
+ * winner (tie rule of bvh.cpp:168-172,219), -1 on miss.  t: HitRecord::distance, TRT_INF on miss.
+ * Either output may be NULL.  With host pointers the call stages through pinned memory in chunks and
+ * overlaps copies with kernels; it returns after the results are in the output arrays. */
+int trt_trace_closest(trt_scene *scene, const float *rays6, size_t n, int32_t *tri_id, float *t, uint32_t flags);
+
+/* Asynchronous device-pointer form on a caller-provided CUDA stream (cudaStream_t passed as void*).    */
+int trt_trace_closest_async(trt_scene *scene, const float *d_rays6, size_t n, int32_t *d_tri_id, float *d_t,
+                            uint32_t flags, void *stream);
+
+/* Hit attributes the reference stores in HitRecord (bvh.h:7-15) for already-traced rays: hit point
+ * S + d*t (bvh.cpp:191) and shading normal pn (bvh.cpp:223-224, least-squares barycentrics of
+ * triangle.cpp:12-29 in double).  Host pointers. Either output may be NULL. */
+int trt_hit_attributes(trt_scene *scene, const float *rays6, const int32_t *tri_id, const float *t, size_t n,
+                       float *hitpoint3, float *pn3);
+
+/* ---- render: replaces the loop body main.cpp:79-113 (getRay, traverseBVH, shade, accumulate) ----- */
+
+typedef struct trt_render_params {
+    int32_t spp;          /* SAMPLE (main.cpp:12,55): the image is divided by this                       */
+    int32_t sample_begin; /* this call renders samples [sample_begin, sample_end) of every pixel        */
+    int32_t sample_end;   /*   (sample-range sharding across GPUs; 0,spp for the whole job)              */
+    int32_t max_depth;    /* 0 = reference behaviour: unbounded, Russian roulette only (pathtracing.h:12) */
+    uint64_t seed;        /* Philox4x32-10 key; streams are keyed (pixel, sample, bounce, slot)           */
+    int32_t batch_paths;  /* paths in flight per wavefront batch, 0 = default                             */
+    uint32_t flags;       /* TRT_RENDER_*                                                                 */
+} trt_render_params;
+
+#define TRT_RENDER_REFTOPO 1u /* trace with the reference-topology kernel instead of the fast layout */
+
+/* Renders the sample range and writes the reference's image buffer: double[H*W*3], row-major RGB, rows
+ * top to bottom, already divided by spp (main.cpp:74,101-108) — what imshow (main.cpp:19-42) consumes. */
+int trt_render(trt_scene *scene, const trt_render_params *params, double *image_rgb);
+
+/* Multi-GPU building block: ADDS the per-pixel radiance sums (not divided by spp) of the sample range
+ * into a device buffer double[H*W*3] on `stream`; ranks then sum their buffers with one NCCL reduce and
+ * call trt_resolve.  d_accum must be zero-initialised by the caller before the first call. */
+int trt_render_accumulate(trt_scene *scene, const trt_render_params *params, double *d_accum, void *stream);
+
+/* image = accum / spp (main.cpp:101); optional 8-bit gamma-2.2 pack as imshow (main.cpp:30-38).
+ * d_accum device pointer; image_rgb / rgb8 host pointers, either may be NULL. */
+int trt_resolve(trt_scene *scene, const double *d_accum, int32_t spp, double *image_rgb, uint8_t *rgb8,
+                void *stream);
+
+/* ---- introspection ------------------------------------------------------------------------------- */
+
+typedef struct trt_stats {
+    uint64_t rays_closest; /* closest-hit rays traced (primary + bounce) since creation / last reset   */
+    uint64_t rays_shadow;  /* NEE "shadow" rays (closest hit + material compare, pathTracing.cpp:51-58) */
+    uint64_t paths;        /* pixel-samples started                                                     */
+    uint64_t kernel_launches;
+    double last_render_ms; /* device time of the last trt_render / trt_render_accumulate (CUDA events)  */
+    double last_trace_ms;  /* device time of the traversal kernel(s) of the last trt_trace_closest      */
+    int32_t accel_nodes;   /* nodes of the GPU layout                                                   */
+    int32_t accel_leaves;  /* reference leaves (bvh.cpp:43-48) kept as scan units                       */
+    int32_t ref_depth;     /* depth of the reference tree                                               */
+    int32_t device;
+} trt_stats;
+
+int trt_get_stats(trt_scene *scene, trt_stats *out);
+int trt_reset_stats(trt_scene *scene);
+const char *trt_last_error(void);
+int trt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRT_H */

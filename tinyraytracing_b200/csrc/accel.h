@@ -1,0 +1,99 @@
+// GPU acceleration layouts and the device-resident scene (internal header shared by the .cu files).
+#pragma once
+#include "../../include/trt.h"
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+namespace trt
+{
+// Tie key of the "miss" state: above every non-emissive key, below every emissive key (bit 31), so that a hit
+// at exactly t == INF is accepted only for an emissive triangle, as bvh.cpp:219 does.
+#define TRT_MISS_KEY 0x7FFFFFFFu
+
+// per-thread traversal stack entries for the reference topology; scenes whose reference tree is deeper are
+// rejected at trt_scene_create (staircase: depth 59)
+#define TRT_REF_STACK_LIMIT 64
+
+// ---- reference topology, two child boxes per inner node (64 B) --------------------------------------------
+// a = (L.AA.x L.AA.y L.AA.z L.BB.x)  b = (L.BB.y L.BB.z R.AA.x R.AA.y)  c = (R.AA.z R.BB.x R.BB.y R.BB.z)
+// d = (left link, right link, -, -);  link >= 0: inner node index;  link < 0: leaf, ~link = first<<3 | (num-1)
+struct __align__(16) RefNode
+{
+    float4 a, b, c;
+    int4 d;
+};
+
+// Triangle for the intersection test (48 B): (p1.xyz N.x) (p2.xyz N.y) (p3.xyz N.z)
+struct __align__(16) TriGeom
+{
+    float4 p1nx, p2ny, p3nz;
+};
+
+// Shading attributes of a triangle (fetched once per path vertex, not during traversal)
+struct __align__(16) TriShade
+{
+    float vn[9];
+    float vt[6];
+    int32_t mtl;
+};
+
+struct DeviceMaterial
+{
+    float3 Kd, Ks, Tr, radiance;
+    float Ns, Ni;
+    int32_t is_emissive, texture;
+    double area;
+};
+
+struct DeviceLight
+{
+    int32_t material, first_tri, n_tris, _pad;
+};
+
+struct DeviceTexture
+{
+    int32_t rows, cols;
+    const uint8_t *bgr;
+};
+
+struct DeviceCamera
+{
+    float3 eye, llc, horizontal, vertical;
+    int32_t width, height;
+};
+
+// Everything the kernels read, by value in kernel parameters.
+struct SceneView
+{
+    // reference-topology layout
+    const RefNode *ref_nodes;
+    int32_t root_link; // link of the root (leaf link when the whole scene is one leaf); 0x7fffffff = empty scene
+    int32_t n_tris;
+    const TriGeom *tri_geom; // post-build order
+    const uint32_t *tri_key; // tie key, higher wins at equal t
+    const float *tri_v;      // n*9 original vertices (barycentric solve)
+    const TriShade *tri_shade;
+    const DeviceMaterial *materials;
+    const DeviceLight *lights;
+    const float *light_v, *light_vn;
+    const double *light_cum_area;
+    const DeviceTexture *textures;
+    int32_t n_lights, n_materials;
+    double first_light_area; // quirk A.5-1: the static distribution's range (pathTracing.cpp:38)
+    DeviceCamera cam;
+};
+
+struct AccelBuild
+{
+    std::vector<RefNode> ref_nodes;
+    int32_t root_link = 0x7fffffff;
+    std::vector<TriGeom> tri_geom;
+    std::vector<uint32_t> tri_key;
+    int32_t n_leaves = 0, ref_depth = 0;
+};
+
+// Builds the layouts from the reference topology in `desc`. Returns "" or an error text.
+std::string buildAccel(const trt_scene_desc &desc, AccelBuild &out);
+} // namespace trt

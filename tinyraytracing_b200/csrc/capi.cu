@@ -1,0 +1,480 @@
+// The C ABI of include/trt.h: scene upload, blocking / async closest-hit entry points, render entry points.
+#include "scene_impl.h"
+
+#include <algorithm>
+#include <memory>
+#include <cstring>
+#include <mutex>
+
+namespace trt
+{
+static thread_local std::string g_lastError;
+void setLastError(const std::string &s) { g_lastError = s; }
+
+namespace
+{
+template <typename T>
+int upload(trt_scene *s, const T *src, size_t count, const T **dst)
+{
+    *dst = nullptr;
+    if (count == 0)
+        return TRT_OK;
+    void *p = nullptr;
+    TRT_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    s->allocations.push_back(p);
+    TRT_CUDA(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = static_cast<const T *>(p);
+    return TRT_OK;
+}
+
+int fail(int code, const std::string &msg)
+{
+    setLastError(msg);
+    return code;
+}
+
+bool isSm100(int device)
+{
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess)
+        return false;
+    return p.major == 10; // the library ships sm_100a SASS only
+}
+
+// staging for the blocking host-pointer entry point
+constexpr size_t kChunkRays = 1u << 21;
+
+int ensureStaging(trt_scene *s)
+{
+    if (s->chunk_rays)
+        return TRT_OK;
+    for (int b = 0; b < 2; ++b)
+    {
+        TRT_CUDA(cudaMallocHost(&s->stage_in[b], kChunkRays * 6 * sizeof(float)));
+        TRT_CUDA(cudaMallocHost(&s->stage_out[b], kChunkRays * 8));
+        TRT_CUDA(cudaMalloc((void **)&s->d_rays[b], kChunkRays * 6 * sizeof(float)));
+        TRT_CUDA(cudaMalloc((void **)&s->d_id[b], kChunkRays * sizeof(int32_t)));
+        TRT_CUDA(cudaMalloc((void **)&s->d_t[b], kChunkRays * sizeof(float)));
+        TRT_CUDA(cudaEventCreateWithFlags(&s->ev_in[b], cudaEventDisableTiming));
+        TRT_CUDA(cudaEventCreateWithFlags(&s->ev_k[b], cudaEventDisableTiming));
+        TRT_CUDA(cudaEventCreateWithFlags(&s->ev_out[b], cudaEventDisableTiming));
+    }
+    s->chunk_rays = kChunkRays;
+    return TRT_OK;
+}
+
+bool isPinnedOrManaged(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+} // namespace
+} // namespace trt
+
+using namespace trt;
+
+extern "C"
+{
+int trt_version(void) { return TRT_VERSION; }
+const char *trt_last_error(void) { return g_lastError.c_str(); }
+
+int trt_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int i = 0; i < n; ++i)
+        ok += isSm100(i) ? 1 : 0;
+    return ok;
+}
+
+void *trt_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess)
+    {
+        setLastError("cudaMallocHost failed");
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void trt_host_free(void *p)
+{
+    if (p)
+        cudaFreeHost(p);
+}
+
+int trt_scene_create(const trt_scene_desc *desc, int device, trt_scene **out)
+{
+    if (!desc || !out)
+        return fail(TRT_ERR_INVALID, "trt_scene_create: null argument");
+    *out = nullptr;
+    if (desc->n_tris < 0 || desc->n_nodes < 0 || desc->n_materials < 1 || desc->width < 2 || desc->height < 2)
+        return fail(TRT_ERR_INVALID, "trt_scene_create: inconsistent description");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    {
+        cudaGetLastError();
+        return fail(TRT_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
+    }
+    if (device < 0 || device >= ndev || !isSm100(device))
+        return fail(TRT_ERR_NO_DEVICE, "device is not an sm_100 (B200) GPU: this library ships sm_100a code only");
+
+    AccelBuild ab;
+    std::string err = buildAccel(*desc, ab);
+    if (!err.empty())
+        return fail(TRT_ERR_INVALID, "trt_scene_create: " + err);
+    if (ab.ref_depth >= TRT_REF_STACK_LIMIT)
+        return fail(TRT_ERR_LIMIT, "reference tree deeper than the traversal stack (" +
+                                       std::to_string(ab.ref_depth) + " >= " + std::to_string(TRT_REF_STACK_LIMIT) + ")");
+
+    std::unique_ptr<trt_scene> s(new trt_scene());
+    s->device = device;
+    TRT_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    TRT_CUDA(cudaGetDeviceProperties(&prop, device));
+    s->sm_count = prop.multiProcessorCount;
+    TRT_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    TRT_CUDA(cudaStreamCreateWithFlags(&s->copy_in, cudaStreamNonBlocking));
+    TRT_CUDA(cudaStreamCreateWithFlags(&s->copy_out, cudaStreamNonBlocking));
+    TRT_CUDA(cudaEventCreate(&s->ev[0]));
+    TRT_CUDA(cudaEventCreate(&s->ev[1]));
+
+    SceneView &v = s->view;
+    int rc;
+    if ((rc = upload(s.get(), ab.ref_nodes.data(), ab.ref_nodes.size(), &v.ref_nodes)))
+        return rc;
+    if ((rc = upload(s.get(), ab.tri_geom.data(), ab.tri_geom.size(), &v.tri_geom)))
+        return rc;
+    if ((rc = upload(s.get(), ab.tri_key.data(), ab.tri_key.size(), &v.tri_key)))
+        return rc;
+    if ((rc = upload(s.get(), desc->v, (size_t)desc->n_tris * 9, &v.tri_v)))
+        return rc;
+    v.root_link = ab.root_link;
+    v.n_tris = desc->n_tris;
+
+    std::vector<TriShade> shade(desc->n_tris);
+    for (int i = 0; i < desc->n_tris; ++i)
+    {
+        if (desc->vn)
+            std::memcpy(shade[i].vn, desc->vn + (size_t)i * 9, 36);
+        else
+            std::memset(shade[i].vn, 0, 36);
+        if (desc->vt)
+            std::memcpy(shade[i].vt, desc->vt + (size_t)i * 6, 24);
+        else
+            std::memset(shade[i].vt, 0, 24);
+        shade[i].mtl = desc->mtl[i];
+    }
+    if ((rc = upload(s.get(), shade.data(), shade.size(), &v.tri_shade)))
+        return rc;
+
+    std::vector<DeviceTexture> tex(desc->n_textures);
+    for (int i = 0; i < desc->n_textures; ++i)
+    {
+        const trt_texture &t = desc->textures[i];
+        if (t.rows < 1 || t.cols < 1 || !t.bgr)
+            return fail(TRT_ERR_INVALID, "trt_scene_create: empty texture");
+        tex[i].rows = t.rows, tex[i].cols = t.cols;
+        if ((rc = upload(s.get(), t.bgr, (size_t)t.rows * t.cols * 3, &tex[i].bgr)))
+            return rc;
+    }
+    if ((rc = upload(s.get(), tex.data(), tex.size(), &v.textures)))
+        return rc;
+
+    std::vector<DeviceMaterial> mats(desc->n_materials);
+    for (int i = 0; i < desc->n_materials; ++i)
+    {
+        const trt_material &m = desc->materials[i];
+        if (m.texture >= desc->n_textures)
+            return fail(TRT_ERR_INVALID, "trt_scene_create: material texture index out of range");
+        mats[i].Kd = make_float3(m.Kd[0], m.Kd[1], m.Kd[2]);
+        mats[i].Ks = make_float3(m.Ks[0], m.Ks[1], m.Ks[2]);
+        mats[i].Tr = make_float3(m.Tr[0], m.Tr[1], m.Tr[2]);
+        mats[i].radiance = make_float3(m.radiance[0], m.radiance[1], m.radiance[2]);
+        mats[i].Ns = m.Ns, mats[i].Ni = m.Ni;
+        mats[i].is_emissive = m.is_emissive, mats[i].texture = m.texture;
+        mats[i].area = m.area;
+    }
+    if ((rc = upload(s.get(), mats.data(), mats.size(), &v.materials)))
+        return rc;
+    v.n_materials = desc->n_materials;
+
+    std::vector<DeviceLight> lights(desc->n_lights);
+    for (int i = 0; i < desc->n_lights; ++i)
+    {
+        const trt_light &l = desc->lights[i];
+        if (l.material < 0 || l.material >= desc->n_materials || l.first_tri < 0 || l.n_tris < 0 ||
+            l.first_tri + l.n_tris > desc->n_light_tris)
+            return fail(TRT_ERR_INVALID, "trt_scene_create: light out of range");
+        lights[i] = DeviceLight{l.material, l.first_tri, l.n_tris, 0};
+    }
+    if ((rc = upload(s.get(), lights.data(), lights.size(), &v.lights)))
+        return rc;
+    if ((rc = upload(s.get(), desc->light_v, (size_t)desc->n_light_tris * 9, &v.light_v)))
+        return rc;
+    if ((rc = upload(s.get(), desc->light_vn, (size_t)desc->n_light_tris * 9, &v.light_vn)))
+        return rc;
+    if ((rc = upload(s.get(), desc->light_cum_area, (size_t)desc->n_light_tris, &v.light_cum_area)))
+        return rc;
+    v.n_lights = desc->n_lights;
+    v.first_light_area = desc->n_lights > 0 ? desc->materials[desc->lights[0].material].area : 0.0;
+
+    v.cam.eye = make_float3(desc->eye[0], desc->eye[1], desc->eye[2]);
+    v.cam.llc = make_float3(desc->lower_left_corner[0], desc->lower_left_corner[1], desc->lower_left_corner[2]);
+    v.cam.horizontal = make_float3(desc->horizontal[0], desc->horizontal[1], desc->horizontal[2]);
+    v.cam.vertical = make_float3(desc->vertical[0], desc->vertical[1], desc->vertical[2]);
+    v.cam.width = desc->width, v.cam.height = desc->height;
+    s->width = desc->width, s->height = desc->height;
+
+    s->stats.accel_nodes = (int32_t)ab.ref_nodes.size();
+    s->stats.accel_leaves = ab.n_leaves;
+    s->stats.ref_depth = ab.ref_depth;
+    s->stats.device = device;
+    *out = s.release();
+    return TRT_OK;
+}
+
+void trt_scene_destroy(trt_scene *s)
+{
+    if (!s)
+        return;
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();
+    destroyWavefront(s);
+    for (void *p : s->allocations)
+        cudaFree(p);
+    for (int b = 0; b < 2; ++b)
+    {
+        if (s->stage_in[b])
+            cudaFreeHost(s->stage_in[b]);
+        if (s->stage_out[b])
+            cudaFreeHost(s->stage_out[b]);
+        cudaFree(s->d_rays[b]), cudaFree(s->d_id[b]), cudaFree(s->d_t[b]);
+        if (s->ev_in[b])
+            cudaEventDestroy(s->ev_in[b]), cudaEventDestroy(s->ev_k[b]), cudaEventDestroy(s->ev_out[b]);
+    }
+    if (s->ev[0])
+        cudaEventDestroy(s->ev[0]), cudaEventDestroy(s->ev[1]);
+    if (s->stream)
+        cudaStreamDestroy(s->stream), cudaStreamDestroy(s->copy_in), cudaStreamDestroy(s->copy_out);
+    delete s;
+}
+
+int trt_trace_closest_async(trt_scene *s, const float *d_rays6, size_t n, int32_t *d_id, float *d_t, uint32_t flags,
+                            void *stream)
+{
+    if (!s || (!d_rays6 && n))
+        return fail(TRT_ERR_INVALID, "trt_trace_closest_async: null argument");
+    TRT_CUDA(cudaSetDevice(s->device));
+    return launchClosest(s, d_rays6, n, d_id, d_t, flags, static_cast<cudaStream_t>(stream));
+}
+
+int trt_trace_closest(trt_scene *s, const float *rays6, size_t n, int32_t *tri_id, float *t, uint32_t flags)
+{
+    if (!s || (!rays6 && n))
+        return fail(TRT_ERR_INVALID, "trt_trace_closest: null argument");
+    TRT_CUDA(cudaSetDevice(s->device));
+    if (flags & TRT_TRACE_DEVICE_PTRS)
+    {
+        TRT_CUDA(cudaEventRecord(s->ev[0], s->stream));
+        int rc = launchClosest(s, rays6, n, tri_id, t, flags, s->stream);
+        if (rc)
+            return rc;
+        TRT_CUDA(cudaEventRecord(s->ev[1], s->stream));
+        TRT_CUDA(cudaStreamSynchronize(s->stream));
+        float ms = 0;
+        TRT_CUDA(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
+        s->stats.last_trace_ms = ms;
+        return TRT_OK;
+    }
+    // host pointers: chunked, double-buffered pipeline  H2D (copy_in) -> kernel (stream) -> D2H (copy_out)
+    int rc = ensureStaging(s);
+    if (rc)
+        return rc;
+    const bool in_pinned = isPinnedOrManaged(rays6);
+    const bool id_pinned = tri_id && isPinnedOrManaged(tri_id), t_pinned = t && isPinnedOrManaged(t);
+    const size_t C = s->chunk_rays;
+    const size_t nchunks = (n + C - 1) / C;
+    // pending D2H of chunk c-2 must be drained (and unstaged) before buffer b is reused
+    auto drain = [&](size_t c) -> int {
+        const int b = (int)(c & 1);
+        const size_t off = c * C, m = std::min(C, n - off);
+        TRT_CUDA(cudaEventSynchronize(s->ev_out[b]));
+        if (tri_id && !id_pinned)
+            std::memcpy(tri_id + off, s->stage_out[b], m * 4);
+        if (t && !t_pinned)
+            std::memcpy(t + off, (char *)s->stage_out[b] + C * 4, m * 4);
+        return TRT_OK;
+    };
+    TRT_CUDA(cudaEventRecord(s->ev[0], s->stream));
+    for (size_t c = 0; c < nchunks; ++c)
+    {
+        const int b = (int)(c & 1);
+        const size_t off = c * C, m = std::min(C, n - off);
+        if (c >= 2 && (rc = drain(c - 2)))
+            return rc;
+        const float *src = rays6 + off * 6;
+        if (!in_pinned)
+        {
+            std::memcpy(s->stage_in[b], src, m * 24);
+            src = static_cast<const float *>(s->stage_in[b]);
+        }
+        // the kernel that last read d_rays[b] (chunk c-2) must be done before it is overwritten
+        TRT_CUDA(cudaStreamWaitEvent(s->copy_in, s->ev_k[b], 0));
+        TRT_CUDA(cudaMemcpyAsync(s->d_rays[b], src, m * 24, cudaMemcpyHostToDevice, s->copy_in));
+        TRT_CUDA(cudaEventRecord(s->ev_in[b], s->copy_in));
+        TRT_CUDA(cudaStreamWaitEvent(s->stream, s->ev_in[b], 0));
+        TRT_CUDA(cudaStreamWaitEvent(s->stream, s->ev_out[b], 0)); // outputs of chunk c-2 copied out
+        if ((rc = launchClosest(s, s->d_rays[b], m, s->d_id[b], s->d_t[b], flags, s->stream)))
+            return rc;
+        TRT_CUDA(cudaEventRecord(s->ev_k[b], s->stream));
+        TRT_CUDA(cudaStreamWaitEvent(s->copy_out, s->ev_k[b], 0));
+        if (tri_id)
+            TRT_CUDA(cudaMemcpyAsync(id_pinned ? (void *)(tri_id + off) : s->stage_out[b], s->d_id[b], m * 4,
+                                     cudaMemcpyDeviceToHost, s->copy_out));
+        if (t)
+            TRT_CUDA(cudaMemcpyAsync(t_pinned ? (void *)(t + off) : (void *)((char *)s->stage_out[b] + C * 4), s->d_t[b],
+                                     m * 4, cudaMemcpyDeviceToHost, s->copy_out));
+        TRT_CUDA(cudaEventRecord(s->ev_out[b], s->copy_out));
+    }
+    TRT_CUDA(cudaEventRecord(s->ev[1], s->stream));
+    for (size_t c = (nchunks >= 2 ? nchunks - 2 : 0); c < nchunks; ++c)
+        if ((rc = drain(c)))
+            return rc;
+    TRT_CUDA(cudaStreamSynchronize(s->stream));
+    float ms = 0;
+    TRT_CUDA(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
+    s->stats.last_trace_ms = ms;
+    return TRT_OK;
+}
+
+int trt_hit_attributes(trt_scene *s, const float *rays6, const int32_t *tri_id, const float *t, size_t n,
+                       float *hitpoint3, float *pn3)
+{
+    if (!s || ((!rays6 || !tri_id || !t) && n))
+        return fail(TRT_ERR_INVALID, "trt_hit_attributes: null argument");
+    if (n == 0)
+        return TRT_OK;
+    TRT_CUDA(cudaSetDevice(s->device));
+    float *d_r = nullptr, *d_t = nullptr, *d_h = nullptr, *d_p = nullptr;
+    int32_t *d_i = nullptr;
+    int rc = TRT_OK;
+    auto cleanup = [&] { cudaFree(d_r), cudaFree(d_t), cudaFree(d_h), cudaFree(d_p), cudaFree(d_i); };
+#define TRT_TRY(call)                                                                                               \
+    do                                                                                                              \
+    {                                                                                                               \
+        cudaError_t e__ = (call);                                                                                   \
+        if (e__ != cudaSuccess)                                                                                     \
+        {                                                                                                           \
+            setLastError(std::string(#call) + ": " + cudaGetErrorString(e__));                                      \
+            cleanup();                                                                                              \
+            return TRT_ERR_CUDA;                                                                                    \
+        }                                                                                                           \
+    } while (0)
+    TRT_TRY(cudaMalloc((void **)&d_r, n * 24));
+    TRT_TRY(cudaMalloc((void **)&d_t, n * 4));
+    TRT_TRY(cudaMalloc((void **)&d_i, n * 4));
+    TRT_TRY(cudaMalloc((void **)&d_h, n * 12));
+    TRT_TRY(cudaMalloc((void **)&d_p, n * 12));
+    TRT_TRY(cudaMemcpyAsync(d_r, rays6, n * 24, cudaMemcpyHostToDevice, s->stream));
+    TRT_TRY(cudaMemcpyAsync(d_t, t, n * 4, cudaMemcpyHostToDevice, s->stream));
+    TRT_TRY(cudaMemcpyAsync(d_i, tri_id, n * 4, cudaMemcpyHostToDevice, s->stream));
+    rc = launchHitAttributes(s, d_r, d_i, d_t, n, d_h, d_p, s->stream);
+    if (rc == TRT_OK)
+    {
+        if (hitpoint3)
+            TRT_TRY(cudaMemcpyAsync(hitpoint3, d_h, n * 12, cudaMemcpyDeviceToHost, s->stream));
+        if (pn3)
+            TRT_TRY(cudaMemcpyAsync(pn3, d_p, n * 12, cudaMemcpyDeviceToHost, s->stream));
+        TRT_TRY(cudaStreamSynchronize(s->stream));
+    }
+    cleanup();
+    return rc;
+#undef TRT_TRY
+}
+
+int trt_render_accumulate(trt_scene *s, const trt_render_params *p, double *d_accum, void *stream)
+{
+    if (!s || !p || !d_accum)
+        return fail(TRT_ERR_INVALID, "trt_render_accumulate: null argument");
+    if (p->spp < 1 || p->sample_begin < 0 || p->sample_end < p->sample_begin || p->sample_end > p->spp || p->max_depth < 0)
+        return fail(TRT_ERR_INVALID, "trt_render_accumulate: bad sample range / spp / max_depth");
+    TRT_CUDA(cudaSetDevice(s->device));
+    return renderAccumulate(s, *p, d_accum, static_cast<cudaStream_t>(stream));
+}
+
+int trt_resolve(trt_scene *s, const double *d_accum, int32_t spp, double *image_rgb, uint8_t *rgb8, void *stream_)
+{
+    if (!s || !d_accum || spp < 1)
+        return fail(TRT_ERR_INVALID, "trt_resolve: bad argument");
+    TRT_CUDA(cudaSetDevice(s->device));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t n = (size_t)s->width * s->height * 3;
+    double *d_img = nullptr;
+    uint8_t *d_rgb = nullptr;
+    TRT_CUDA(cudaMalloc((void **)&d_img, n * sizeof(double)));
+    if (cudaMalloc((void **)&d_rgb, n) != cudaSuccess)
+    {
+        cudaFree(d_img);
+        return fail(TRT_ERR_CUDA, "cudaMalloc failed");
+    }
+    int rc = resolveImage(s, d_accum, spp, d_img, d_rgb, stream);
+    cudaError_t e = cudaSuccess;
+    if (rc == TRT_OK && image_rgb)
+        e = cudaMemcpyAsync(image_rgb, d_img, n * sizeof(double), cudaMemcpyDeviceToHost, stream);
+    if (rc == TRT_OK && e == cudaSuccess && rgb8)
+        e = cudaMemcpyAsync(rgb8, d_rgb, n, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(stream);
+    cudaFree(d_img), cudaFree(d_rgb);
+    if (rc == TRT_OK && e != cudaSuccess)
+        return fail(TRT_ERR_CUDA, std::string("trt_resolve: ") + cudaGetErrorString(e));
+    return rc;
+}
+
+int trt_render(trt_scene *s, const trt_render_params *p, double *image_rgb)
+{
+    if (!s || !p || !image_rgb)
+        return fail(TRT_ERR_INVALID, "trt_render: null argument");
+    TRT_CUDA(cudaSetDevice(s->device));
+    const size_t n = (size_t)s->width * s->height * 3;
+    double *d_accum = nullptr;
+    TRT_CUDA(cudaMalloc((void **)&d_accum, n * sizeof(double)));
+    int rc = TRT_OK;
+    if (cudaMemsetAsync(d_accum, 0, n * sizeof(double), s->stream) != cudaSuccess)
+        rc = fail(TRT_ERR_CUDA, "cudaMemsetAsync failed");
+    if (rc == TRT_OK)
+        rc = trt_render_accumulate(s, p, d_accum, s->stream);
+    if (rc == TRT_OK)
+        rc = trt_resolve(s, d_accum, p->spp, image_rgb, nullptr, s->stream);
+    cudaFree(d_accum);
+    return rc;
+}
+
+int trt_get_stats(trt_scene *s, trt_stats *out)
+{
+    if (!s || !out)
+        return fail(TRT_ERR_INVALID, "trt_get_stats: null argument");
+    *out = s->stats;
+    return TRT_OK;
+}
+
+int trt_reset_stats(trt_scene *s)
+{
+    if (!s)
+        return fail(TRT_ERR_INVALID, "trt_reset_stats: null argument");
+    s->stats.rays_closest = s->stats.rays_shadow = s->stats.paths = s->stats.kernel_launches = 0;
+    return TRT_OK;
+}
+}

@@ -1,0 +1,58 @@
+// trt_scene: the device-resident scene behind the opaque handle of include/trt.h (internal).
+#pragma once
+#include "accel.h"
+
+#include <string>
+#include <vector>
+
+namespace trt
+{
+void setLastError(const std::string &s);
+
+#define TRT_CUDA(call)                                                                                              \
+    do                                                                                                              \
+    {                                                                                                               \
+        cudaError_t e__ = (call);                                                                                   \
+        if (e__ != cudaSuccess)                                                                                     \
+        {                                                                                                           \
+            trt::setLastError(std::string(#call) + ": " + cudaGetErrorString(e__));                                 \
+            return TRT_ERR_CUDA;                                                                                    \
+        }                                                                                                           \
+    } while (0)
+
+struct Wavefront; // wavefront.cu
+}
+
+struct trt_scene
+{
+    int device = 0;
+    int sm_count = 148;
+    trt::SceneView view{};
+    std::vector<void *> allocations; // every cudaMalloc owned by the scene
+    cudaStream_t stream = nullptr;   // library-owned stream for the blocking entry points
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    // pinned staging for pageable host buffers (two chunks in flight)
+    void *stage_in[2] = {nullptr, nullptr}, *stage_out[2] = {nullptr, nullptr};
+    float *d_rays[2] = {nullptr, nullptr};
+    int32_t *d_id[2] = {nullptr, nullptr};
+    float *d_t[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    size_t chunk_rays = 0;
+    trt::Wavefront *wf = nullptr;
+    trt_stats stats{};
+    int width = 0, height = 0;
+};
+
+namespace trt
+{
+// trace.cu
+int launchClosest(trt_scene *s, const float *d_rays6, size_t n, int32_t *d_id, float *d_t, uint32_t flags,
+                  cudaStream_t stream);
+int launchHitAttributes(trt_scene *s, const float *d_rays6, const int32_t *d_id, const float *d_t, size_t n,
+                        float *d_hitp3, float *d_pn3, cudaStream_t stream);
+// wavefront.cu
+int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, cudaStream_t stream);
+int resolveImage(trt_scene *s, const double *d_accum, int spp, double *d_image, uint8_t *d_rgb8, cudaStream_t stream);
+void destroyWavefront(trt_scene *s);
+} // namespace trt

@@ -1,0 +1,92 @@
+// Fixed-batch closest-hit kernels (BASELINE config 2): one thread per ray over the device-resident scene.
+#include "scene_impl.h"
+#include "traverse.cuh"
+#include "barycentric.cuh"
+
+namespace trt
+{
+namespace
+{
+constexpr int kTraceBlock = 128;
+
+__device__ __forceinline__ void loadRay(const float *rays6, size_t i, float3 &S, float3 &d)
+{
+    // 24-byte records: three aligned 8-byte loads per ray
+    const float2 *p = reinterpret_cast<const float2 *>(rays6 + i * 6);
+    const float2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    S = f3(a.x, a.y, b.x);
+    d = f3(b.y, c.x, c.y);
+}
+
+template <int MODE> // 0: ordered + pruned reference topology, 1: exhaustive reference walk
+__global__ void __launch_bounds__(kTraceBlock) k_closest(SceneView sv, const float *__restrict__ rays6, size_t n,
+                                                         int32_t *__restrict__ out_id, float *__restrict__ out_t)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    float3 S, d;
+    loadRay(rays6, i, S, d);
+    Hit hit;
+    if (MODE == 1)
+        traceRefTopology<true>(sv, S, d, hit);
+    else
+        traceRefTopology<false>(sv, S, d, hit);
+    if (out_id)
+        out_id[i] = hit.id;
+    if (out_t)
+        out_t[i] = hit.t;
+}
+
+__global__ void __launch_bounds__(128) k_hit_attributes(SceneView sv, const float *__restrict__ rays6,
+                                                        const int32_t *__restrict__ id, const float *__restrict__ t,
+                                                        size_t n, float *__restrict__ hitp3, float *__restrict__ pn3)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    float3 P = f3(0.f, 0.f, 0.f), pn = f3(0.f, 0.f, 0.f); // HitRecord defaults (bvh.h:11-13)
+    const int tri = id[i];
+    if (tri >= 0)
+    {
+        float3 S, d;
+        loadRay(rays6, i, S, d);
+        P = S + d * t[i]; // bvh.cpp:191
+        float bx, by, bz;
+        baryLeastSquares(sv.tri_v + (size_t)tri * 9, P, bx, by, bz);
+        pn = shadingNormal(sv.tri_shade[tri].vn, bx, by, bz);
+    }
+    if (hitp3)
+        hitp3[i * 3] = P.x, hitp3[i * 3 + 1] = P.y, hitp3[i * 3 + 2] = P.z;
+    if (pn3)
+        pn3[i * 3] = pn.x, pn3[i * 3 + 1] = pn.y, pn3[i * 3 + 2] = pn.z;
+}
+} // namespace
+
+int launchClosest(trt_scene *s, const float *d_rays6, size_t n, int32_t *d_id, float *d_t, uint32_t flags,
+                  cudaStream_t stream)
+{
+    if (n == 0)
+        return TRT_OK;
+    const unsigned grid = (unsigned)((n + kTraceBlock - 1) / kTraceBlock);
+    if (flags & TRT_TRACE_EXHAUSTIVE)
+        k_closest<1><<<grid, kTraceBlock, 0, stream>>>(s->view, d_rays6, n, d_id, d_t);
+    else
+        k_closest<0><<<grid, kTraceBlock, 0, stream>>>(s->view, d_rays6, n, d_id, d_t);
+    TRT_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    s->stats.rays_closest += n;
+    return TRT_OK;
+}
+
+int launchHitAttributes(trt_scene *s, const float *d_rays6, const int32_t *d_id, const float *d_t, size_t n,
+                        float *d_hitp3, float *d_pn3, cudaStream_t stream)
+{
+    if (n == 0)
+        return TRT_OK;
+    k_hit_attributes<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(s->view, d_rays6, d_id, d_t, n, d_hitp3, d_pn3);
+    TRT_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return TRT_OK;
+}
+} // namespace trt

@@ -1,0 +1,410 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the B200-native TinyRayTracing hot path.
+
+Workload (BASELINE.json configs[1]): the fixed 16 Mi random-ray closest-hit batch against the cornell-box BVH
+(the Cornell shell `test/back` — cornell-box.obj itself is a missing blob in the reference checkout), 1 B200.
+A "step" is one pass of the closest-hit path over the whole batch.
+
+  value     Mrays/s with rays and results resident in HBM (CUDA events on the launching stream)
+  e2e       the same metric through the C-ABI call a host program makes (trt_trace_closest with pinned host
+            buffers): H2D of the rays and D2H of ids + distances inside the timed region
+  roofline  dominant kernel (k_closest) against the measured HBM copy bandwidth, using the ALGORITHMIC bytes
+            per ray B = 48 + 32*A + 48*T of SURVEY §8d (A, T from profiles/algorithmic_work.json)
+  cpu_baseline / --impl reference: the UNMODIFIED reference traverseBVH (oracle/_ref/libref.so) on the box's
+            host cores over a bounded sample of the same rays
+
+N > 1 (torchrun, one rank per GPU): the scene is replicated, every rank traces its own 16 Mi batch (weak
+scaling, no data-path collective: ray batches shard by index); time = max over ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_RAYS = 16 << 20
+SCENE = "back"
+WORKLOAD = ("16Mi-ray closest-hit batch (25% camera / 50% uniform-in-AABB / 25% cosine bounce), cornell-box shell "
+            "example-scenes-cg22/test/back (26 tris; cornell-box.obj is a missing blob)")
+
+
+def env_int(k, d):
+    return int(os.environ.get(k, d))
+
+
+def load_algorithmic_work(scene):
+    p = os.path.join(ROOT, "profiles", "algorithmic_work.json")
+    try:
+        with open(p) as f:
+            w = json.load(f)[scene]
+        return float(w["A"]), float(w["T"])
+    except Exception:
+        return None
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def materialize_scene(tmp):
+    from tinyraytracing_b200 import scenes
+
+    return scenes.materialize(SCENE, tmp, width=512, height=512)
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def reference_rays(ref, n, seed):
+    """Same ray population as the GPU arm, surface points supplied by the reference's own traversal."""
+    from tinyraytracing_b200 import workloads
+
+    cam12 = ref.camera()
+    w, h = ref.image_size()
+    cam = dict(eye=cam12[0:3], llc=cam12[3:6], horizontal=cam12[6:9], vertical=cam12[9:12], width=w, height=h)
+    boxes, _ = ref.bvh_flatten()
+
+    def tracer(rays):
+        t, ids, pn, hp = ref.trace(rays, want_pn=True)
+        return ids, hp, pn
+
+    return workloads.fixed_ray_batch(n, cam, (boxes[0, :3], boxes[0, 3:]), tracer, seed=seed)
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refbridge
+
+    if not refbridge.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref.so not built (run __graft_entry__.build() in the build container)"}))
+        return 0
+    with tempfile.TemporaryDirectory() as tmp:
+        f = materialize_scene(tmp)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)  # the reference loaders print to stdout
+        try:
+            ref = refbridge.RefScene(f["xml"], f["obj"], f["mtl"], f["basedir"])
+        finally:
+            os.dup2(saved, 1)
+        cores = os.cpu_count() or 1
+        # bounded sample: size it so that one step takes about 2 s on this host
+        pilot = reference_rays(ref, 1 << 18, seed=0x5EED0001)
+        t0 = time.perf_counter()
+        ref.trace(pilot, threads=cores)
+        rate = len(pilot) / (time.perf_counter() - t0)
+        n = int(min(N_RAYS, max(1 << 18, rate * 2.0)))
+        rays = reference_rays(ref, n, seed=0x5EED0001)
+        for _ in range(args.warmup):
+            ref.trace(rays[: max(1, n // 8)], threads=cores)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ref.trace(rays, threads=cores)
+        dt = time.perf_counter() - t0
+        mrays = n * args.steps / dt / 1e6
+        sample = "%d rays of the %d-ray batch per step" % (n, N_RAYS)
+        print(json.dumps({
+            "impl": "reference", "metric": "Mrays/s (closest-hit)", "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_step": n, "host_threads": cores},
+            "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import tinyraytracing_b200 as trt
+    from tinyraytracing_b200 import workloads
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = trt.load_library()
+    with tempfile.TemporaryDirectory() as tmp:
+        f = materialize_scene(tmp)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)  # the loaders keep the reference's stdout chatter
+        try:
+            host = trt.HostScene.load(f["xml"], f["obj"], f["mtl"], f["basedir"])
+        finally:
+            os.dup2(saved, 1)
+        dev = trt.DeviceScene(host, local)
+
+        def tracer(rays):
+            ids, t = dev.trace_closest(rays)
+            hp, pn = dev.hit_attributes(rays, ids, t)
+            return ids, hp, pn
+
+        n = args.rays
+        rays = workloads.fixed_ray_batch(n, host.camera(), host.root_box(), tracer, seed=0x5EED0001 + rank)
+        # pinned host buffers for the e2e leg, device buffers for the resident leg
+        p_rays, p_id, p_t = lib.trt_host_alloc(n * 24), lib.trt_host_alloc(n * 4), lib.trt_host_alloc(n * 4)
+        C.memmove(p_rays, rays.ctypes.data, n * 24)
+        d_rays = torch.from_numpy(rays).cuda()
+        d_id = torch.empty(n, dtype=torch.int32, device="cuda")
+        d_t = torch.empty(n, dtype=torch.float32, device="cuda")
+        stream = torch.cuda.current_stream()
+        sp = stream.cuda_stream
+
+        def step_resident():
+            dev.trace_closest_async(d_rays.data_ptr(), n, d_id.data_ptr(), d_t.data_ptr(), args.flags, sp)
+
+        def step_e2e():
+            dev.trace_closest_ptr(p_rays, n, p_id, p_t, args.flags)
+
+        def barrier():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def timed(fn, events):
+            for _ in range(args.warmup):
+                fn()
+            barrier()
+            dev.reset_stats()
+            clocks = ClockSampler(local)
+            clocks.start()
+            if events:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(args.steps):
+                    fn()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+            else:
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    fn()
+                torch.cuda.synchronize()
+                ms = (time.perf_counter() - t0) * 1e3
+            ck = clocks.stop()
+            launches = dev.stats()["kernel_launches"]
+            barrier()
+            if world > 1:
+                tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                ms = float(tm.item())
+            return ms, ck, launches
+
+        ms_res, clocks, launches = timed(step_resident, events=True)
+        ms_e2e, clocks_e2e, _ = timed(step_e2e, events=False)
+
+        # sanity of what was timed: results of both legs agree and really hit geometry
+        ids_host = np.ctypeslib.as_array(C.cast(p_id, C.POINTER(C.c_int32)), (n,))
+        assert np.array_equal(ids_host, d_id.cpu().numpy()), "resident and e2e legs disagree"
+        hit_fraction = float((ids_host >= 0).mean())
+
+        total_rays = float(n) * world * args.steps
+        value = total_rays / (ms_res * 1e-3) / 1e6
+        e2e = total_rays / (ms_e2e * 1e-3) / 1e6
+        out = {
+            "metric": "Mrays/s (closest-hit)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": n, "hit_fraction": hit_fraction,
+                       "l2": "inputs (%d MB rays + %d MB results per step) exceed the 126 MB L2" % (n * 24 >> 20, n * 8 >> 20),
+                       "traversal": {0: "default", 2: "exhaustive", 4: "reftopo"}.get(args.flags, str(args.flags))},
+            "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": n * 24 * world, "d2h_bytes_per_step": n * 8 * world,
+                    "ms_per_step": ms_e2e / args.steps, "timer": "host wall clock around the blocking C-ABI call"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        work = load_algorithmic_work(SCENE)
+        peak, which = measured_peak_gbs()
+        if work:
+            A, T = work
+            bytes_per_ray = 48 + 32 * A + 48 * T
+            achieved = bytes_per_ray * n / (ms_res / args.steps * 1e-3) / 1e9  # per launch = per step on one GPU
+            out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                               "traffic": None, "kernel": "k_closest", "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
+                               "bytes_per_ray": bytes_per_ray, "A": A, "T": T,
+                               "note": "scene is L1/L2 resident (2 kB): the HBM-denominated figure is for cross-config comparison, SURVEY §8d"}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(f, rays)
+        if args.extra and rank == 0 and world == 1:
+            out["extra"] = extra_measurements(args, tmp)
+        for p in (p_rays, p_id, p_t):
+            lib.trt_host_free(p)
+        dev.close()
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def cpu_baseline(files, rays):
+    """The unmodified reference traversal (oracle/_ref) on the host cores, bounded sample of the same rays."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    cores = os.cpu_count() or 1
+    import refbridge
+
+    if refbridge.available():
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)
+        try:
+            ref = refbridge.RefScene(files["xml"], files["obj"], files["mtl"], files["basedir"])
+        finally:
+            os.dup2(saved, 1)
+        trace, kind = (lambda r: ref.trace(r, threads=cores)), "reference"
+    else:
+        import oraclelib
+
+        orc = oraclelib.OracleScene(oraclelib.parsed_scene(SCENE, 512, 512))
+        trace, kind = (lambda r: orc.trace(r, threads=cores)), "port"
+    pilot = rays[: 1 << 18]
+    t0 = time.perf_counter()
+    trace(pilot)
+    rate = len(pilot) / (time.perf_counter() - t0)
+    n = int(min(len(rays), max(1 << 18, rate * 10.0)))  # about 10 s of CPU work
+    t0 = time.perf_counter()
+    trace(rays[:n])
+    dt = time.perf_counter() - t0
+    return {"value": n / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind,
+            "sample": "first %d rays of the %d-ray batch, %d OpenMP threads" % (n, len(rays), cores)}
+
+
+def extra_measurements(args, tmp):
+    """Other BASELINE configs, reported beside the headline (not the bench line's value)."""
+    import torch
+
+    import tinyraytracing_b200 as trt
+    from tinyraytracing_b200 import scenes, workloads
+
+    out = {}
+    for name, (w, h, spp) in {"back": (512, 512, 16), "veach-mis": (1280, 720, 16), "staircase": (1280, 720, 8)}.items():
+        f = scenes.materialize(name, os.path.join(tmp, "x_" + name), width=w, height=h)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)
+        try:
+            host = trt.HostScene.load(f["xml"], f["obj"], f["mtl"], f["basedir"])
+        finally:
+            os.dup2(saved, 1)
+        dev = trt.DeviceScene(host, 0)
+
+        def tracer(rays):
+            ids, t = dev.trace_closest(rays)
+            hp, pn = dev.hit_attributes(rays, ids, t)
+            return ids, hp, pn
+
+        n = 4 << 20
+        rays = workloads.fixed_ray_batch(n, host.camera(), host.root_box(), tracer)
+        d_rays = torch.from_numpy(rays).cuda()
+        d_id = torch.empty(n, dtype=torch.int32, device="cuda")
+        d_t = torch.empty(n, dtype=torch.float32, device="cuda")
+        sp = torch.cuda.current_stream().cuda_stream
+        for _ in range(2):
+            dev.trace_closest_async(d_rays.data_ptr(), n, d_id.data_ptr(), d_t.data_ptr(), args.flags, sp)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            dev.trace_closest_async(d_rays.data_ptr(), n, d_id.data_ptr(), d_t.data_ptr(), args.flags, sp)
+        e1.record()
+        torch.cuda.synchronize()
+        rec = {"closest_hit_mrays": 3 * n / (e0.elapsed_time(e1) * 1e-3) / 1e6, "tris": host.n_tris}
+        dev.render(1, seed=1)  # warm-up (allocates the wavefront buffers)
+        dev.reset_stats()
+        dev.render(spp, seed=1)
+        st = dev.stats()
+        rays_total = st["rays_closest"] + st["rays_shadow"]
+        rec["render"] = {"width": w, "height": h, "spp": spp, "ms": st["last_render_ms"],
+                         "spp_per_s": spp / (st["last_render_ms"] * 1e-3),
+                         "mrays": rays_total / (st["last_render_ms"] * 1e-3) / 1e6,
+                         "rays_closest": st["rays_closest"], "rays_shadow": st["rays_shadow"],
+                         "kernel_launches": st["kernel_launches"]}
+        out[name] = rec
+        dev.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rays", type=int, default=N_RAYS)
+    ap.add_argument("--flags", type=int, default=0, help="TRT_TRACE_* traversal flags (0 = default layout)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--extra", action="store_true", help="also measure the other scenes and the render path")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    return run_reference(args) if args.impl == "reference" else run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

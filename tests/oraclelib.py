@@ -1,0 +1,215 @@
+"""ctypes view of oracle/liboracle.so (tier B: deterministic CPU restatement) + scene-pack helpers.
+Test infrastructure only: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIBORACLE = os.path.join(ROOT, "oracle", "liboracle.so")
+
+
+class OrcMaterial(C.Structure):
+    _fields_ = [("Kd", C.c_float * 3), ("Ks", C.c_float * 3), ("Tr", C.c_float * 3), ("Ns", C.c_float),
+                ("Ni", C.c_float), ("texture", C.c_int32)]
+
+
+class OrcTexture(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("bgr", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIBORACLE)
+        vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
+        L.orc_scene_create.restype = vp
+        L.orc_scene_create.argtypes = [i32, vp, vp, vp, vp, i32, C.POINTER(OrcMaterial), i32, vp, vp, i32,
+                                       C.POINTER(OrcTexture), vp, vp, vp, C.c_float, i32, i32, i32]
+        L.orc_scene_destroy.argtypes = [vp]
+        L.orc_num_nodes.argtypes = [vp]
+        L.orc_get_order.argtypes = [vp, vp]
+        L.orc_get_derived.argtypes = [vp, vp, vp, vp, vp]
+        L.orc_get_nodes.argtypes = [vp, vp, vp]
+        L.orc_get_camera.argtypes = [vp, vp]
+        L.orc_bvh_stats.argtypes = [vp, vp, vp, vp]
+        L.orc_trace.argtypes = [vp, vp, i64, vp, vp, vp, vp, i32]
+        L.orc_trace_counts.argtypes = [vp, vp, i64, i32, vp, vp, vp, i32]
+        L.orc_render.argtypes = [vp, i32, i32, i32, i32, u64, vp, vp, i32]
+        L.orc_philox4x32_10.argtypes = [vp, vp, vp]
+        L.orc_uniform.restype = C.c_double
+        L.orc_uniform.argtypes = [u64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.orc_primary_ray.argtypes = [vp, i32, i32, i32, u64, vp]
+        _lib = L
+    return _lib
+
+
+def available():
+    return os.path.exists(LIBORACLE)
+
+
+def parsed_scene(name, width=None, height=None):
+    """Parsed (pre-build, OBJ-order) scene arrays straight from scenes/<name>.npz — independent of both the
+    product's C++ loader and the reference's: numbers are converted with numpy float32 (== stof)."""
+    import cv2
+
+    z = np.load(os.path.join(ROOT, "scenes", name + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    faces = z["faces"]  # (n, 3 corners, 3 slots v/vt/vn or v/vn/vt)
+    v, vn, vt = z["v"], z["vn"], z["vt"]
+    s2, s3 = (2, 1) if not meta["isvnvt"] else (1, 2)  # column of vn, column of vt
+    tri_v = v[faces[:, :, 0] - 1].reshape(-1, 9)
+    tri_vn = vn[faces[:, :, s2] - 1].reshape(-1, 9)
+    tri_vt = vt[faces[:, :, s3] - 1].reshape(-1, 6)
+    # materials: names in order of first appearance: lights (xml), obj usemtl, mtl newmtl
+    xml = meta["xml"]
+    names = []
+    for l in xml["lights"]:
+        if l["mtlname"] not in names:
+            names.append(l["mtlname"])
+    for nme in meta["obj_mtl_names"]:
+        if nme not in names:
+            names.append(nme)
+    mats = {}
+    cur = ""
+    tex_files = []
+    for tok in meta["mtl"]:
+        k = tok[0]
+        if k == "newmtl":
+            cur = tok[1]
+        elif k in ("Kd", "Ks", "Tr"):
+            mats.setdefault(cur, {})[k] = [np.float32(x) for x in tok[1:4]]
+        elif k in ("Ns", "Ni"):
+            mats.setdefault(cur, {})[k] = np.float32(tok[1])
+        elif k == "map_Kd":
+            mats.setdefault(cur, {})["map_Kd"] = tok[1]
+            if tok[1] not in tex_files:
+                tex_files.append(tok[1])
+    for nme in mats:
+        if nme not in names:
+            names.append(nme)
+    textures = [cv2.imdecode(z["jpeg:" + f], cv2.IMREAD_COLOR) for f in tex_files]
+    materials = []
+    for nme in names:
+        m = mats.get(nme, {})
+        materials.append(dict(name=nme, Kd=m.get("Kd", [0, 0, 0]), Ks=m.get("Ks", [0, 0, 0]), Tr=m.get("Tr", [0, 0, 0]),
+                              Ns=m.get("Ns", 1.0), Ni=m.get("Ni", 1.0),
+                              texture=tex_files.index(m["map_Kd"]) if "map_Kd" in m else -1))
+    face_mtl = np.array([names.index(meta["obj_mtl_names"][i]) for i in z["face_mtl"]], np.int32)
+    lights = []
+    for l in xml["lights"]:
+        rs = l["radiance"].split(",")
+        lights.append((names.index(l["mtlname"]), [np.float32(x) for x in rs[:3]]))
+    f3 = lambda d: np.array([np.float32(d["x"]), np.float32(d["y"]), np.float32(d["z"])], np.float32)
+    cam = xml["camera"]
+    return dict(name=name, v=tri_v, vn=tri_vn, vt=tri_vt, mtl=face_mtl, materials=materials, lights=lights,
+                textures=textures, eye=f3(xml["eye"]), lookat=f3(xml["lookat"]), up=f3(xml["up"]),
+                fovy=np.float32(cam["fovy"]), width=int(width or cam["width"]), height=int(height or cam["height"]))
+
+
+class OracleScene:
+    def __init__(self, ps, leaf_num=8):
+        """ps: dict as returned by parsed_scene() (or hand-made with the same keys)."""
+        L = lib()
+        self.ps = ps
+        n = len(ps["v"])
+        self.n = n
+        v = np.ascontiguousarray(ps["v"], np.float32)
+        vn = np.ascontiguousarray(ps["vn"], np.float32)
+        vt = np.ascontiguousarray(ps["vt"], np.float32)
+        mtl = np.ascontiguousarray(ps["mtl"], np.int32)
+        M = (OrcMaterial * len(ps["materials"]))()
+        for i, m in enumerate(ps["materials"]):
+            M[i].Kd[:] = [float(x) for x in m["Kd"]]
+            M[i].Ks[:] = [float(x) for x in m["Ks"]]
+            M[i].Tr[:] = [float(x) for x in m["Tr"]]
+            M[i].Ns, M[i].Ni, M[i].texture = float(m["Ns"]), float(m["Ni"]), int(m.get("texture", -1))
+        lm = np.array([l[0] for l in ps["lights"]], np.int32)
+        lr = np.array([l[1] for l in ps["lights"]], np.float32).reshape(-1, 3)
+        self._tex = [np.ascontiguousarray(t, np.uint8) for t in ps.get("textures", [])]
+        T = (OrcTexture * max(1, len(self._tex)))()
+        for i, t in enumerate(self._tex):
+            T[i].rows, T[i].cols, T[i].bgr = t.shape[0], t.shape[1], t.ctypes.data
+        e, la, u = (np.ascontiguousarray(ps[k], np.float32) for k in ("eye", "lookat", "up"))
+        self.h = L.orc_scene_create(n, v.ctypes.data, vn.ctypes.data, vt.ctypes.data, mtl.ctypes.data, len(M), M,
+                                    len(lm), lm.ctypes.data, lr.ctypes.data, len(self._tex), T, e.ctypes.data,
+                                    la.ctypes.data, u.ctypes.data, float(ps["fovy"]), ps["width"], ps["height"], leaf_num)
+        self.width, self.height = ps["width"], ps["height"]
+
+    def order(self):
+        p = np.zeros(self.n, np.int32)
+        lib().orc_get_order(self.h, p.ctypes.data)
+        return p
+
+    def derived(self):
+        n = self.n
+        normal, center = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+        area, em = np.zeros(n, np.float64), np.zeros(n, np.int32)
+        lib().orc_get_derived(self.h, normal.ctypes.data, center.ctypes.data, area.ctypes.data, em.ctypes.data)
+        return dict(normal=normal, center=center, area=area, emissive=em)
+
+    def nodes(self):
+        n = lib().orc_num_nodes(self.h)
+        b, l = np.zeros((n, 6), np.float32), np.zeros((n, 4), np.int32)
+        lib().orc_get_nodes(self.h, b.ctypes.data, l.ctypes.data)
+        return b, l
+
+    def camera(self):
+        o = np.zeros(12, np.float32)
+        lib().orc_get_camera(self.h, o.ctypes.data)
+        return o
+
+    def bvh_stats(self):
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        lib().orc_bvh_stats(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+    def trace(self, rays, threads=0, want_pn=False):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        n = len(rays)
+        t, ids = np.zeros(n, np.float32), np.zeros(n, np.int32)
+        pn = np.zeros((n, 3), np.float32) if want_pn else None
+        hp = np.zeros((n, 3), np.float32) if want_pn else None
+        lib().orc_trace(self.h, rays.ctypes.data, n, t.ctypes.data, ids.ctypes.data,
+                        pn.ctypes.data if want_pn else None, hp.ctypes.data if want_pn else None, threads)
+        return (ids, t, pn, hp) if want_pn else (ids, t)
+
+    def trace_counts(self, rays, mode, threads=0):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        n = len(rays)
+        b, t = C.c_uint64(), C.c_uint64()
+        ids = np.zeros(n, np.int32)
+        lib().orc_trace_counts(self.h, rays.ctypes.data, n, mode, C.byref(b), C.byref(t), ids.ctypes.data, threads)
+        return b.value / max(n, 1), t.value / max(n, 1), ids
+
+    def render(self, spp, seed=0, max_depth=0, sample_begin=0, sample_end=None, threads=0):
+        img = np.zeros((self.height, self.width, 3), np.float64)
+        counts = (C.c_uint64 * 2)(0, 0)
+        lib().orc_render(self.h, spp, sample_begin, spp if sample_end is None else sample_end, max_depth, seed,
+                         img.ctypes.data, counts, threads)
+        return img, (counts[0], counts[1])
+
+    def primary_ray(self, i, j, k, seed=0):
+        r = np.zeros(6, np.float32)
+        lib().orc_primary_ray(self.h, i, j, k, seed, r.ctypes.data)
+        return r
+
+    def __del__(self):
+        try:
+            lib().orc_scene_destroy(self.h)
+        except Exception:
+            pass
+
+
+def philox(ctr, key):
+    c, k, o = np.array(ctr, np.uint32), np.array(key, np.uint32), np.zeros(4, np.uint32)
+    lib().orc_philox4x32_10(c.ctypes.data, k.ctypes.data, o.ctypes.data)
+    return o
+
+
+def uniform(seed, pixel, sample, depth, slot):
+    return lib().orc_uniform(seed, pixel, sample, depth, slot)

@@ -1,0 +1,122 @@
+"""Parity of the CUDA closest-hit path (through the C ABI) against the oracle: bit-exact triangle ids and
+distance bits on the BASELINE config-2 ray population, in every traversal mode, plus edge cases."""
+import numpy as np
+import pytest
+
+import tinyraytracing_b200 as trt
+from conftest import SCENES, make_rays
+
+pytestmark = pytest.mark.gpu
+
+MODES = {"default": 0, "reftopo": trt.TRACE_REFTOPO, "exhaustive": trt.TRACE_EXHAUSTIVE}
+
+
+@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("mode", list(MODES))
+def test_closest_hit_bit_exact(name, mode, host_scenes, oracle_scenes, device_scenes):
+    rays = make_rays(host_scenes[name], oracle_scenes[name], 1 << 20, seed=0x5EED0001)
+    oid, ot = oracle_scenes[name].trace(rays)
+    ids, t = device_scenes[name].trace_closest(rays, MODES[mode])
+    bad = np.flatnonzero(ids != oid)
+    assert len(bad) == 0, "%d id mismatches, first ray %d gpu %d oracle %d" % (len(bad), bad[0], ids[bad[0]], oid[bad[0]])
+    assert np.array_equal(t.view(np.uint32), ot.view(np.uint32))
+    assert (ids >= 0).sum() > len(rays) // 4  # the batch really hits geometry
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_hit_attributes(name, host_scenes, oracle_scenes, device_scenes):
+    rays = make_rays(host_scenes[name], oracle_scenes[name], 1 << 16, seed=11)
+    oid, ot, opn, ohp = oracle_scenes[name].trace(rays, want_pn=True)
+    ids, t = device_scenes[name].trace_closest(rays)
+    hp, pn = device_scenes[name].hit_attributes(rays, ids, t)
+    hit = ids >= 0
+    assert np.array_equal(hp[hit].view(np.uint32), ohp[hit].view(np.uint32))  # S + d*t in float: bit-exact
+    ok = np.isfinite(opn[hit]).all(axis=1)
+    # pn goes through a double least-squares solve (Eigen QR in the reference): same algorithm, tolerance 1e-6
+    assert np.abs(pn[hit][ok] - opn[hit][ok]).max() <= 1e-6
+    assert (~hit).sum() == 0 or (np.all(hp[~hit] == 0) and np.all(pn[~hit] == 0))  # HitRecord defaults on a miss
+
+
+def test_edge_cases(host_scenes, oracle_scenes, device_scenes):
+    name = "veach-mis"
+    dev, orc, host = device_scenes[name], oracle_scenes[name], host_scenes[name]
+    # empty batch
+    ids, t = dev.trace_closest(np.zeros((0, 6), np.float32))
+    assert len(ids) == 0 and len(t) == 0
+    # single ray, and a ragged size that is not a multiple of the block / chunk
+    for n in (1, 33, 1000003 % 4099):
+        rays = make_rays(host, orc, max(n, 4), seed=n)[:n]
+        ids, t = dev.trace_closest(rays)
+        oid, ot = orc.trace(rays)
+        assert np.array_equal(ids, oid) and np.array_equal(t.view(np.uint32), ot.view(np.uint32))
+    # axis-parallel directions (zero components -> +-inf reciprocals, inf*0 = NaN slabs), NaN / zero directions,
+    # origins exactly on box faces and on surfaces
+    lo, hi = host.root_box()
+    rng = np.random.default_rng(5)
+    o = rng.uniform(lo, hi, (6000, 3)).astype(np.float32)
+    d = np.zeros((6000, 3), np.float32)
+    d[np.arange(6000), rng.integers(0, 3, 6000)] = rng.choice([-1.0, 1.0], 6000)
+    d[:500, 1] = -0.0
+    o[1000:1500, 0] = lo[0]  # on the root box face
+    o[1500:2000, 1] = hi[1]
+    special = np.concatenate([o, d], 1)
+    special[2000:2100, 3:] = 0.0       # zero direction
+    special[2100:2200, 3:] = np.nan    # NaN direction (normalize of a zero vector in the reference)
+    special[2200:2300, :3] = np.inf    # garbage origin
+    for flags in (0, trt.TRACE_REFTOPO, trt.TRACE_EXHAUSTIVE):
+        ids, t = dev.trace_closest(special, flags)
+        oid, ot = orc.trace(special)
+        assert np.array_equal(ids, oid)
+        assert np.array_equal(t.view(np.uint32), ot.view(np.uint32))
+
+
+def test_pinned_and_device_pointer_entry_points(host_scenes, oracle_scenes, device_scenes):
+    import ctypes as C
+
+    name = "back"
+    dev, orc, host = device_scenes[name], oracle_scenes[name], host_scenes[name]
+    n = (1 << 21) + 12345  # more than one staging chunk, ragged tail
+    rays = make_rays(host, orc, n, seed=3)
+    oid, ot = orc.trace(rays)
+    lib = trt.load_library()
+    # pinned host buffers: the library DMAs straight from / to them
+    pr, pi, pt = lib.trt_host_alloc(n * 24), lib.trt_host_alloc(n * 4), lib.trt_host_alloc(n * 4)
+    assert pr and pi and pt
+    C.memmove(pr, rays.ctypes.data, n * 24)
+    dev.trace_closest_ptr(pr, n, pi, pt)
+    ids = np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_int32)), (n,)).copy()
+    t = np.ctypeslib.as_array(C.cast(pt, C.POINTER(C.c_float)), (n,)).copy()
+    for p in (pr, pi, pt):
+        lib.trt_host_free(p)
+    assert np.array_equal(ids, oid) and np.array_equal(t.view(np.uint32), ot.view(np.uint32))
+    # pageable path gives the same
+    ids2, t2 = dev.trace_closest(rays)
+    assert np.array_equal(ids2, oid) and np.array_equal(t2.view(np.uint32), ot.view(np.uint32))
+    # device pointers through torch (plumbing only)
+    import torch
+
+    dr = torch.from_numpy(rays).cuda()
+    di = torch.empty(n, dtype=torch.int32, device="cuda")
+    dt = torch.empty(n, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    dev.trace_closest_ptr(dr.data_ptr(), n, di.data_ptr(), dt.data_ptr(), trt.TRACE_DEVICE_PTRS)
+    assert np.array_equal(di.cpu().numpy(), oid) and np.array_equal(dt.cpu().numpy().view(np.uint32), ot.view(np.uint32))
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_full_size_batch_properties(name, host_scenes, oracle_scenes, device_scenes):
+    """BASELINE config 2 at its full size (16 Mi rays): the pruned walk equals the exhaustive reference walk
+    (order / pruning independence), misses carry (-1, INF), hits lie in [5e-4, INF], and a bounded sample is
+    checked against the oracle."""
+    n = 16 << 20
+    rays = make_rays(host_scenes[name], oracle_scenes[name], n, seed=0x5EED0001)
+    dev = device_scenes[name]
+    ids, t = dev.trace_closest(rays)
+    ids_x, t_x = dev.trace_closest(rays, trt.TRACE_EXHAUSTIVE)
+    assert np.array_equal(ids, ids_x) and np.array_equal(t.view(np.uint32), t_x.view(np.uint32))
+    miss = ids < 0
+    assert np.all(t[miss] == trt.INF) and np.all(t[~miss] >= np.float32(0.0005)) and np.all(t[~miss] <= trt.INF)
+    assert ids.max() < host_scenes[name].n_tris
+    sel = np.random.default_rng(1).choice(n, 1 << 19, replace=False)
+    oid, ot = oracle_scenes[name].trace(rays[sel])
+    assert np.array_equal(ids[sel], oid) and np.array_equal(t[sel].view(np.uint32), ot.view(np.uint32))

@@ -1,16 +1,599 @@
-// placeholder until the wavefront integrator lands (next commit)
+// Wavefront path tracer: the loop body main.cpp:88-108 + shade / nextRay / Sample / RR (pathTracing.cpp:3-209)
+// as a sequence of kernels over a batch of paths held in HBM (SoA), one iteration per path depth:
+//
+//   k_raygen      (K1)  main.cpp:88-95 + Camera::getRay           -> ray[slot], queue = all slots
+//   k_trace       (K2)  traverseBVH for the queue                  -> hit[slot]
+//   k_shade       (K3)  shade(): emissive return, Kd/texture, per-light NEE sample (emits "shadow" rays),
+//                       RR, nextRay/Sample -> next ray, throughput weight, next queue (warp-aggregated append)
+//   k_shadow      (K4)  pathTracing.cpp:51-58: closest hit of the light sample ray; the sample counts only if
+//                       the CLOSEST hit's material is the light's material (not an any-hit test)
+//   k_accumulate  (K5)  L[slot] += throughput * sum(visible light samples, XML order); throughput *= weight
+//   k_deposit           after the batch: accum[pixel] += sum over the batch's samples of L (double, fixed order)
+//   k_resolve     (K6)  accum / spp (main.cpp:101) and the gamma-2.2 8-bit pack of imshow (main.cpp:30-38)
+//
+// A path's slot = (sample_in_batch * W*H + pixel): pixel / sample never need storing, each pixel-sample is
+// owned by exactly one slot, so there are no floating-point atomics and the image is bit-reproducible for a
+// given (seed, spp) whatever the batch size or GPU count (per-sample sums are added in double, sample order).
+//
+// Random numbers: Philox4x32-10, key = seed, counter = (pixel, sample, depth, slot >> 1) — twin of the
+// oracle's generator (oracle/oracle.cpp), see DESIGN.md §5 for the slot table.
 #include "scene_impl.h"
+#include "traverse.cuh"
+#include "barycentric.cuh"
+
+#include <algorithm>
+
 namespace trt
 {
-int renderAccumulate(trt_scene *, const trt_render_params &, double *, cudaStream_t)
+namespace
 {
-    setLastError("render path not built yet");
-    return TRT_ERR_INVALID;
-}
-int resolveImage(trt_scene *, const double *, int, double *, uint8_t *, cudaStream_t)
+constexpr int kBlock = 128;
+constexpr int kMaxLights = 32;
+constexpr float kPI = 3.1415926f; // pathtracing.h:11
+constexpr float kPRR = 0.8f;      // pathtracing.h:12
+enum RayType
 {
-    setLastError("render path not built yet");
-    return TRT_ERR_INVALID;
+    DIFFUSE = 0,
+    SPECULAR = 1,
+    TRANSMISSION = 2,
+    INVALID = 3,
+    CAMERA = 4
+};
+enum Slot
+{
+    S_JITTER_X = 0,
+    S_JITTER_Y = 1,
+    S_RR = 2,
+    S_FRESNEL = 3,
+    S_LOBE = 4,
+    S_PHI = 5,
+    S_THETA = 6,
+    S_LIGHT0 = 8
+};
+
+struct WfBuffers
+{
+    float4 *ray_o, *ray_d; // ray_d.w = ray type (int bits) the path arrived with
+    int32_t *hit_id;
+    float *hit_t;
+    float4 *thr, *L, *weight;
+    uint32_t *nee_mask;
+    int32_t *queue[2];
+    float4 *sh_o, *sh_d; // sh_o.w = contribution index (slot*n_lights + light), sh_d.w = light material
+    float4 *sh_contrib;  // [slot*n_lights + light]
+    int32_t *counters;   // [0],[1]: queue sizes (ping-pong), [2]: shadow queue size
+};
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r)
+    {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0, c1 = lo1, c2 = n2, c3 = lo0;
+        k0 += 0x9E3779B9u, k1 += 0xBB67AE85u;
+    }
+    out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
 }
-void destroyWavefront(trt_scene *) {}
+
+struct Rng
+{
+    uint32_t k0, k1, pixel, sample, depth;
+    // both uniforms of one block: u[0] from words (0,1), u[1] from words (2,3)
+    __device__ __forceinline__ void block(uint32_t blk, double u[2]) const
+    {
+        uint32_t o[4];
+        philox4x32_10(pixel, sample, depth, blk, k0, k1, o);
+        u[0] = (double)(((uint64_t)o[0] << 21) | (uint64_t)(o[1] >> 11)) * (1.0 / 9007199254740992.0);
+        u[1] = (double)(((uint64_t)o[2] << 21) | (uint64_t)(o[3] >> 11)) * (1.0 / 9007199254740992.0);
+    }
+};
+
+__device__ __forceinline__ float3 xyz(float4 v) { return f3(v.x, v.y, v.z); }
+__device__ __forceinline__ float4 xyzw(float3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
+
+// ------------------------------------------------------------------------------------------------ K1
+__global__ void __launch_bounds__(kBlock) k_raygen(SceneView sv, WfBuffers wf, int n_paths, int sample0, uint64_t seed)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_paths)
+        return;
+    const int W = sv.cam.width, H = sv.cam.height, npix = W * H;
+    const int pix = slot % npix, k = sample0 + slot / npix;
+    const int i = pix / W, j = pix % W;
+    Rng rng{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)pix, (uint32_t)k, 0u};
+    double u[2];
+    rng.block(0, u);
+    // main.cpp:88-93
+    double x = double(j) / double(W - 1.0);
+    double y = double(H - i) / double(H - 1.0);
+    x += (u[0] - 0.5f) / double(W);
+    y += (u[1] - 0.5f) / double(H);
+    const float sx = (float)x, sy = (float)y;
+    // camera.cpp:19-28
+    const float3 d = normalize3(sv.cam.llc + sx * sv.cam.horizontal + sy * sv.cam.vertical - sv.cam.eye);
+    wf.ray_o[slot] = xyzw(sv.cam.eye, 0.f);
+    wf.ray_d[slot] = xyzw(d, __int_as_float(CAMERA));
+    wf.thr[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+    wf.L[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    wf.queue[0][slot] = slot;
+    if (slot == 0)
+    {
+        wf.counters[0] = n_paths;
+        wf.counters[1] = 0;
+        wf.counters[2] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K2 / K4
+template <bool REFTOPO>
+__device__ __forceinline__ void traceAny(const SceneView &sv, float3 S, float3 d, Hit &hit)
+{
+    traceRefTopology<false>(sv, S, d, hit);
+}
+
+template <bool REFTOPO>
+__global__ void __launch_bounds__(kBlock) k_trace(SceneView sv, WfBuffers wf, int qsel)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= wf.counters[qsel])
+        return;
+    const int slot = wf.queue[qsel][i];
+    const float3 S = xyz(wf.ray_o[slot]), d = xyz(wf.ray_d[slot]);
+    Hit hit;
+    traceAny<REFTOPO>(sv, S, d, hit);
+    wf.hit_id[slot] = hit.id;
+    wf.hit_t[slot] = hit.t;
+}
+
+template <bool REFTOPO>
+__global__ void __launch_bounds__(kBlock) k_shadow(SceneView sv, WfBuffers wf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= wf.counters[2])
+        return;
+    const float4 o = wf.sh_o[i], dd = wf.sh_d[i];
+    Hit hit;
+    traceAny<REFTOPO>(sv, xyz(o), xyz(dd), hit);
+    // pathTracing.cpp:54-58: visible iff the closest hit's material is the light's material
+    const bool visible = hit.id >= 0 && sv.tri_shade[hit.id].mtl == __float_as_int(dd.w);
+    if (!visible)
+        wf.sh_contrib[__float_as_int(o.w)] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------ K3
+// pathTracing.cpp:111-145
+__device__ __forceinline__ float3 sampleLobe(float3 direction, int ray_type, double Ns, double u_phi, double u_theta)
+{
+    const double phi = u_phi * 2 * (double)kPI;
+    double theta;
+    if (ray_type == DIFFUSE)
+        theta = asin(sqrt(u_theta));
+    else
+        theta = acos(pow(u_theta, (double)1 / (Ns + 1)));
+    double st, ct, sp, cp;
+    sincos(theta, &st, &ct);
+    sincos(phi, &sp, &cp);
+    const float3 sample = f3((float)(st * cp), (float)ct, (float)(st * sp));
+    float3 front;
+    if (fabsf(direction.x) > fabsf(direction.y))
+        front = normalize3(f3(direction.z, 0.f, -direction.x));
+    else
+        front = normalize3(f3(0.f, -direction.z, direction.y));
+    const float3 right = cross3(direction, front);
+    return normalize3(((right * sample.x) + (direction * sample.y)) + (front * sample.z));
+}
+
+__device__ __forceinline__ float3 reflect3(float3 I, float3 N) { return I - N * dot3(N, I) * 2.0f; }
+
+__device__ __forceinline__ void appendQueue(int32_t *counter, int32_t *queue, bool pred, int value)
+{
+    // warp-aggregated append: one atomic per warp
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0)
+        return;
+    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader)
+        base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred)
+        queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
+}
+
+__global__ void __launch_bounds__(kBlock) k_shade(SceneView sv, WfBuffers wf, int qsel, int depth, int max_depth,
+                                                  int sample0, uint64_t seed)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < wf.counters[qsel];
+    bool survives = false;
+    int slot = 0;
+    if (active)
+    {
+        slot = wf.queue[qsel][i];
+        const int tri = wf.hit_id[slot];
+        uint32_t mask = 0;
+        float4 weight = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 rd4 = wf.ray_d[slot];
+        const int via = __float_as_int(rd4.w);
+        if (tri >= 0)
+        {
+            const TriShade ts = sv.tri_shade[tri];
+            const DeviceMaterial m = sv.materials[ts.mtl];
+            if (m.is_emissive)
+            {
+                // :9-12 returns the radiance; DIFFUSE / SPECULAR arrivals drop it (:87-94), camera and
+                // TRANSMISSION arrivals keep it (main.cpp:101, :95-96)
+                if (via == CAMERA || via == TRANSMISSION)
+                {
+                    const float4 T = wf.thr[slot];
+                    float4 L = wf.L[slot];
+                    L.x += T.x * m.radiance.x, L.y += T.y * m.radiance.y, L.z += T.z * m.radiance.z;
+                    wf.L[slot] = L;
+                }
+            }
+            else
+            {
+                const int npix = sv.cam.width * sv.cam.height;
+                Rng rng{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(slot % npix), (uint32_t)(sample0 + slot / npix),
+                        (uint32_t)depth};
+                const float3 S = xyz(wf.ray_o[slot]), d = xyz(rd4);
+                const float3 wi = -d;
+                const float3 P = S + d * wf.hit_t[slot]; // bvh.cpp:191
+                float bx, by, bz;
+                baryLeastSquares(sv.tri_v + (size_t)tri * 9, P, bx, by, bz);
+                const float3 pn = shadingNormal(ts.vn, bx, by, bz); // bvh.cpp:223-224
+                float3 Kd = m.Kd;
+                if (m.texture >= 0) // :17-26
+                {
+                    const double col = (ts.vt[0] * bx + ts.vt[2] * by) + ts.vt[4] * bz;
+                    const double row = (ts.vt[1] * bx + ts.vt[3] * by) + ts.vt[5] * bz;
+                    const double irow = row - floor(row), icol = col - floor(col);
+                    const DeviceTexture tx = sv.textures[m.texture];
+                    const int r = (int)(irow * tx.rows), c = (int)(icol * tx.cols);
+                    const uint8_t *px = tx.bgr + ((size_t)r * tx.cols + c) * 3;
+                    Kd = f3((float)((double)px[2] / 255), (float)((double)px[1] / 255), (float)((double)px[0] / 255));
+                }
+
+                // ---- direct illumination :33-75
+                for (int li = 0; li < sv.n_lights; ++li)
+                {
+                    const DeviceLight lt = sv.lights[li];
+                    double u0[2];
+                    rng.block(4 + 2 * li, u0);
+                    const double rnd = u0[0] * sv.first_light_area; // quirk A.5-1 (:38)
+                    // first light triangle whose cumulative area exceeds rnd (linear walk of :40-42 as a
+                    // binary search: the cumulative areas are non-decreasing)
+                    int lo = 0, hi = lt.n_tris;
+                    const double *cum = sv.light_cum_area + lt.first_tri;
+                    while (lo < hi)
+                    {
+                        const int mid = (lo + hi) >> 1;
+                        if (rnd < cum[mid])
+                            hi = mid;
+                        else
+                            lo = mid + 1;
+                    }
+                    if (lo >= lt.n_tris)
+                        continue;
+                    double u1[2];
+                    rng.block(5 + 2 * li, u1);
+                    const double rnd1 = u0[1], rnd2 = u1[0], rnd3 = u1[1];
+                    const double rs = (rnd1 + rnd2) + rnd3;
+                    const float p1 = (float)(rnd1 / rs), p2 = (float)(rnd2 / rs), p3 = (float)(rnd3 / rs);
+                    const float *lv = sv.light_v + (size_t)(lt.first_tri + lo) * 9;
+                    const float *ln = sv.light_vn + (size_t)(lt.first_tri + lo) * 9;
+                    const float3 light_p = (f3(lv[0], lv[1], lv[2]) * p1 + f3(lv[3], lv[4], lv[5]) * p2) + f3(lv[6], lv[7], lv[8]) * p3;
+                    const float3 light_n =
+                        normalize3((f3(ln[0], ln[1], ln[2]) * p1 + f3(ln[3], ln[4], ln[5]) * p2) + f3(ln[6], ln[7], ln[8]) * p3);
+                    const float3 wo = normalize3(light_p - P);
+                    const float wo_pn = dot3(wo, pn);
+                    if (!(wo_pn > 0.f)) // :60 — the sample cannot contribute: the shadow ray is not traced
+                        continue;
+                    const DeviceMaterial lm = sv.materials[lt.material];
+                    const float pdf_light = (float)(double(1) / lm.area);
+                    const float cos_theta_p = fabsf(dot3(wo, light_n));
+                    const float cos_theta = fabsf(wo_pn / length3(pn));
+                    const float3 diff = light_p - P;
+                    const float len2 = dot3(diff, diff);
+                    const float3 intensity = (((lm.radiance * cos_theta_p) * cos_theta) / len2) / pdf_light;
+                    const float3 h = normalize3((wi + wo) * 0.5f);
+                    const double cos_alpha = fmax((double)dot3(pn, h), 0.0);
+                    const float spec = (float)pow(cos_alpha, (double)m.Ns);
+                    const float3 brdf = (Kd / kPI) + (((m.Ks * (m.Ns + 2.0f)) * spec) / (2.0f * kPI));
+                    const float3 contrib = intensity * brdf;
+                    const int cidx = slot * sv.n_lights + li;
+                    wf.sh_contrib[cidx] = xyzw(contrib, 0.f);
+                    const int sidx = atomicAdd(&wf.counters[2], 1);
+                    wf.sh_o[sidx] = xyzw(P, __int_as_float(cidx));
+                    wf.sh_d[sidx] = xyzw(wo, __int_as_float(lt.material));
+                    mask |= 1u << li;
+                }
+
+                // ---- indirect :78-99
+                const bool may_bounce = (max_depth == 0) || (depth + 1 < max_depth);
+                double ur[2];
+                rng.block(1, ur);
+                if (may_bounce && ur[0] < (double)kPRR) // RR(): :104-109
+                {
+                    // nextRay(): :147-209
+                    const float3 ray_direction = d; // -wi
+                    int type = INVALID;
+                    float3 ndir = f3(0.f, 0.f, 0.f);
+                    bool decided = false;
+                    if (m.Ni > 1.f)
+                    {
+                        double n1, n2;
+                        const double cos_in = (double)dot3(ray_direction, pn);
+                        float3 normal;
+                        if (cos_in > 0)
+                            normal = -pn, n1 = (double)m.Ni, n2 = 1.0;
+                        else
+                            normal = pn, n1 = 1.0, n2 = (double)m.Ni;
+                        const double q = (n1 - n2) / (n1 + n2);
+                        const double rf0 = q * q;
+                        const double a = (double)1.0f - fabs(cos_in);
+                        const double fresnel = rf0 + ((double)1.0f - rf0) * (((a * a) * (a * a)) * a);
+                        if (fresnel < ur[1])
+                        {
+                            const float eta = (float)(n1 / n2);
+                            const float dv = dot3(normal, ray_direction);
+                            const float k = 1.0f - eta * eta * (1.0f - dv * dv);
+                            if (k >= 0.0f)
+                                ndir = eta * ray_direction - (eta * dv + sqrtf(k)) * normal;
+                            if (ndir.x != 0.f || ndir.y != 0.f || ndir.z != 0.f)
+                                type = TRANSMISSION;
+                            else
+                                ndir = reflect3(ray_direction, normal), type = SPECULAR;
+                            decided = true;
+                        }
+                    }
+                    if (!decided)
+                    {
+                        const double Kd_len = (double)length3(m.Kd), Ks_len = (double)length3(m.Ks);
+                        const double kd = Kd_len / (Kd_len + Ks_len), ks = Ks_len / (Kd_len + Ks_len);
+                        double ul[2], ut[2];
+                        rng.block(2, ul);
+                        const double p = ul[0];
+                        if (p < kd)
+                        {
+                            rng.block(3, ut);
+                            ndir = sampleLobe(pn, DIFFUSE, (double)m.Ns, ul[1], ut[0]);
+                            type = DIFFUSE;
+                        }
+                        else if (m.Ns > 1.f && p < kd + ks)
+                        {
+                            rng.block(3, ut);
+                            ndir = sampleLobe(reflect3(ray_direction, pn), SPECULAR, (double)m.Ns, ul[1], ut[0]);
+                            type = SPECULAR;
+                        }
+                    }
+                    if (type != INVALID) // the reference traces the INVALID ray too and discards it (:81-82)
+                    {
+                        const float3 w = (type == TRANSMISSION) ? m.Tr : Kd; // SPECULAR also weights by Kd (:92-93)
+                        weight = xyzw(w / kPRR, 0.f);
+                        wf.ray_o[slot] = xyzw(P, 0.f);
+                        wf.ray_d[slot] = xyzw(ndir, __int_as_float(type));
+                        survives = true;
+                    }
+                }
+            }
+        }
+        wf.nee_mask[slot] = mask;
+        wf.weight[slot] = weight;
+    }
+    appendQueue(&wf.counters[qsel ^ 1], wf.queue[qsel ^ 1], survives, slot);
+}
+
+// ------------------------------------------------------------------------------------------------ K5
+__global__ void __launch_bounds__(kBlock) k_accumulate(SceneView sv, WfBuffers wf, int qsel)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= wf.counters[qsel])
+        return;
+    const int slot = wf.queue[qsel][i];
+    uint32_t mask = wf.nee_mask[slot];
+    float4 T = wf.thr[slot];
+    if (mask)
+    {
+        float3 Ldir = f3(0.f, 0.f, 0.f);
+        while (mask)
+        {
+            const int li = __ffs(mask) - 1;
+            mask &= mask - 1;
+            Ldir = Ldir + xyz(wf.sh_contrib[slot * sv.n_lights + li]); // L_dir += ..., lights in XML order (:70)
+        }
+        float4 L = wf.L[slot];
+        L.x += T.x * Ldir.x, L.y += T.y * Ldir.y, L.z += T.z * Ldir.z;
+        wf.L[slot] = L;
+    }
+    const float4 w = wf.weight[slot];
+    T.x *= w.x, T.y *= w.y, T.z *= w.z;
+    wf.thr[slot] = T;
+}
+
+__global__ void k_reset_counters(WfBuffers wf, int qnext)
+{
+    // before k_shade of an iteration: the queue it fills and the shadow queue start empty
+    wf.counters[qnext] = 0;
+    wf.counters[2] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_deposit(WfBuffers wf, double *accum, int npix, int samples_in_batch)
+{
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= npix)
+        return;
+    double r = 0, g = 0, b = 0;
+    for (int s = 0; s < samples_in_batch; ++s)
+    {
+        const float4 L = wf.L[(size_t)s * npix + pix];
+        r += (double)L.x, g += (double)L.y, b += (double)L.z;
+    }
+    accum[(size_t)pix * 3 + 0] += r;
+    accum[(size_t)pix * 3 + 1] += g;
+    accum[(size_t)pix * 3 + 2] += b;
+}
+
+__global__ void __launch_bounds__(256) k_resolve(const double *accum, size_t n, int spp, double *image, uint8_t *rgb8)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const double v = accum[i] / (double)spp;
+    if (image)
+        image[i] = v;
+    if (rgb8)
+    {
+        // main.cpp:34: (unsigned char)clamp(pow(v, 1.0f / 2.2f) * 255, 0.0, 255.0)
+        double g = pow(v, (double)(1.0f / 2.2f)) * 255;
+        g = (g < 0.0) ? 0.0 : g;
+        g = (255.0 < g) ? 255.0 : g;
+        rgb8[i] = (uint8_t)g;
+    }
+}
+} // namespace
+
+struct Wavefront
+{
+    WfBuffers buf{};
+    int capacity = 0; // paths
+    int n_lights = 0;
+    std::vector<void *> allocs;
+    int32_t *h_counters = nullptr; // pinned
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+void destroyWavefront(trt_scene *s)
+{
+    if (!s->wf)
+        return;
+    for (void *p : s->wf->allocs)
+        cudaFree(p);
+    if (s->wf->h_counters)
+        cudaFreeHost(s->wf->h_counters);
+    if (s->wf->ev0)
+        cudaEventDestroy(s->wf->ev0), cudaEventDestroy(s->wf->ev1);
+    delete s->wf;
+    s->wf = nullptr;
+}
+
+static int ensureWavefront(trt_scene *s, int paths)
+{
+    if (s->wf && s->wf->capacity >= paths)
+        return TRT_OK;
+    destroyWavefront(s);
+    Wavefront *w = new Wavefront();
+    s->wf = w;
+    w->capacity = paths;
+    w->n_lights = std::max(1, s->view.n_lights);
+    const size_t N = (size_t)paths, NL = N * w->n_lights;
+    auto alloc = [&](void **p, size_t bytes) -> int {
+        TRT_CUDA(cudaMalloc(p, bytes));
+        w->allocs.push_back(*p);
+        return TRT_OK;
+    };
+    int rc;
+    WfBuffers &b = w->buf;
+    if ((rc = alloc((void **)&b.ray_o, N * 16)) || (rc = alloc((void **)&b.ray_d, N * 16)) ||
+        (rc = alloc((void **)&b.hit_id, N * 4)) || (rc = alloc((void **)&b.hit_t, N * 4)) ||
+        (rc = alloc((void **)&b.thr, N * 16)) || (rc = alloc((void **)&b.L, N * 16)) ||
+        (rc = alloc((void **)&b.weight, N * 16)) || (rc = alloc((void **)&b.nee_mask, N * 4)) ||
+        (rc = alloc((void **)&b.queue[0], N * 4)) || (rc = alloc((void **)&b.queue[1], N * 4)) ||
+        (rc = alloc((void **)&b.sh_o, NL * 16)) || (rc = alloc((void **)&b.sh_d, NL * 16)) ||
+        (rc = alloc((void **)&b.sh_contrib, NL * 16)) || (rc = alloc((void **)&b.counters, 16)))
+        return rc;
+    TRT_CUDA(cudaMallocHost((void **)&w->h_counters, 16));
+    TRT_CUDA(cudaEventCreate(&w->ev0));
+    TRT_CUDA(cudaEventCreate(&w->ev1));
+    return TRT_OK;
+}
+
+int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, cudaStream_t stream)
+{
+    const int W = s->width, H = s->height;
+    const long long npix = (long long)W * H;
+    if (s->view.n_lights > kMaxLights)
+    {
+        setLastError("more than 32 lights");
+        return TRT_ERR_LIMIT;
+    }
+    const long long target = p.batch_paths > 0 ? p.batch_paths : (4ll << 20);
+    const int total_samples = p.sample_end - p.sample_begin;
+    if (total_samples <= 0)
+        return TRT_OK;
+    int spb = (int)std::max(1ll, std::min((long long)total_samples, target / npix));
+    if (npix * spb > 0x7fffffffll / std::max(1, s->view.n_lights))
+    {
+        setLastError("batch too large for 32-bit slot indices");
+        return TRT_ERR_LIMIT;
+    }
+    int rc = ensureWavefront(s, (int)(npix * spb));
+    if (rc)
+        return rc;
+    Wavefront *w = s->wf;
+    const WfBuffers &b = w->buf;
+    const bool reftopo = (p.flags & TRT_RENDER_REFTOPO) != 0;
+    TRT_CUDA(cudaEventRecord(w->ev0, stream));
+    for (int s0 = p.sample_begin; s0 < p.sample_end; s0 += spb)
+    {
+        const int ns = std::min(spb, p.sample_end - s0);
+        const int n_paths = (int)(npix * ns);
+        const unsigned grid_all = (unsigned)((n_paths + kBlock - 1) / kBlock);
+        k_raygen<<<grid_all, kBlock, 0, stream>>>(s->view, b, n_paths, s0, p.seed);
+        s->stats.kernel_launches++;
+        s->stats.paths += (uint64_t)n_paths;
+        int live = n_paths, q = 0;
+        for (int depth = 0; live > 0; ++depth)
+        {
+            const unsigned grid = (unsigned)((live + kBlock - 1) / kBlock);
+            if (reftopo)
+                k_trace<true><<<grid, kBlock, 0, stream>>>(s->view, b, q);
+            else
+                k_trace<false><<<grid, kBlock, 0, stream>>>(s->view, b, q);
+            k_reset_counters<<<1, 1, 0, stream>>>(b, q ^ 1);
+            k_shade<<<grid, kBlock, 0, stream>>>(s->view, b, q, depth, p.max_depth, s0, p.seed);
+            TRT_CUDA(cudaMemcpyAsync(w->h_counters, b.counters, 12, cudaMemcpyDeviceToHost, stream));
+            TRT_CUDA(cudaStreamSynchronize(stream));
+            const int n_shadow = w->h_counters[2], next_live = w->h_counters[q ^ 1];
+            s->stats.rays_closest += (uint64_t)live;
+            s->stats.rays_shadow += (uint64_t)n_shadow;
+            s->stats.kernel_launches += 3;
+            if (n_shadow > 0)
+            {
+                const unsigned gs = (unsigned)((n_shadow + kBlock - 1) / kBlock);
+                if (reftopo)
+                    k_shadow<true><<<gs, kBlock, 0, stream>>>(s->view, b);
+                else
+                    k_shadow<false><<<gs, kBlock, 0, stream>>>(s->view, b);
+                s->stats.kernel_launches++;
+            }
+            k_accumulate<<<grid, kBlock, 0, stream>>>(s->view, b, q);
+            s->stats.kernel_launches++;
+            live = next_live;
+            q ^= 1;
+        }
+        k_deposit<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(b, d_accum, (int)npix, ns);
+        s->stats.kernel_launches++;
+        TRT_CUDA(cudaGetLastError());
+    }
+    TRT_CUDA(cudaEventRecord(w->ev1, stream));
+    TRT_CUDA(cudaStreamSynchronize(stream));
+    float ms = 0;
+    TRT_CUDA(cudaEventElapsedTime(&ms, w->ev0, w->ev1));
+    s->stats.last_render_ms = ms;
+    return TRT_OK;
+}
+
+int resolveImage(trt_scene *s, const double *d_accum, int spp, double *d_image, uint8_t *d_rgb8, cudaStream_t stream)
+{
+    const size_t n = (size_t)s->width * s->height * 3;
+    k_resolve<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_accum, n, spp, d_image, d_rgb8);
+    TRT_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return TRT_OK;
+}
 } // namespace trt

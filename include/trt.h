@@ -133,6 +133,11 @@ int trt_trace_closest_async(trt_scene *scene, const float *d_rays6, size_t n, in
 int trt_hit_attributes(trt_scene *scene, const float *rays6, const int32_t *tri_id, const float *t, size_t n,
                        float *hitpoint3, float *pn3);
 
+/* Work done by the default traversal on a host ray batch, summed over rays: out4 = {wide nodes visited, child
+ * box tests, reference leaves scanned, triangles in those leaves}.  Reporting only (rays that take the strict
+ * walk are not counted). */
+int trt_trace_counters(trt_scene *scene, const float *rays6, size_t n, uint64_t out4[4]);
+
 /* ---- render: replaces the loop body main.cpp:79-113 (getRay, traverseBVH, shade, accumulate) ----- */
 
 typedef struct trt_render_params {

@@ -1,0 +1,59 @@
+"""The C-ABI library loads and exports every symbol include/*.h declares; no compute calls (CPU suite)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import tinyraytracing_b200 as trt
+from tinyraytracing_b200 import api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    for h in ("trt.h", "trt_host.h"):
+        txt = open(os.path.join(ROOT, "include", h)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        names |= set(re.findall(r"\b(trt_[a-z0-9_]+)\s*\(", txt))
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    lib = trt.load_library()
+    decl = declared_symbols()
+    assert decl == set(api.EXPORTS), decl ^ set(api.EXPORTS)
+    for s in decl:
+        assert hasattr(lib, s), s
+    assert lib.trt_version() == 100
+
+
+def test_sm100a_sass_is_embedded():
+    """The shared library must carry sm_100a device code (and nothing the driver would have to JIT)."""
+    import shutil
+    import subprocess
+
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    out = subprocess.run(["cuobjdump", "-lelf", trt.library_path()], stdout=subprocess.PIPE, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback_without_gpu(host_scenes):
+    lib = trt.load_library()
+    if lib.trt_device_count() > 0:
+        pytest.skip("a B200 is present: the no-device error path cannot be exercised")
+    with pytest.raises(trt.TrtError) as e:
+        trt.DeviceScene(host_scenes["back"], 0)
+    assert "(-2)" in str(e.value)  # TRT_ERR_NO_DEVICE: fails loudly, never computes on the CPU
+
+
+def test_bad_arguments_return_errors_not_exits():
+    lib = trt.load_library()
+    h = C.c_void_p()
+    assert lib.trt_host_scene_load(b"/nonexistent.xml", b"/nonexistent.obj", b"/nonexistent.mtl", b"/tmp", 8, C.byref(h)) == -1
+    assert b"xml" in lib.trt_last_error()
+    assert lib.trt_scene_create(None, 0, C.byref(h)) == -1
+    assert lib.trt_trace_closest(None, None, 0, None, None, 0) == -1
+    assert lib.trt_get_stats(None, None) == -1

@@ -1,0 +1,155 @@
+"""Host side kept by the drop-in surface (loaders + buildBVH, csrc/host) against the reference-generated golden
+fixtures and against the oracle's independent restatement.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+import oraclelib
+import tinyraytracing_b200 as trt
+from conftest import SCENES, SMALL_RES
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_host_build_matches_reference_golden(name, host_scenes):
+    g = np.load(os.path.join(GOLD, name + "_closest.npz"))
+    h = host_scenes[name]
+    tr = h.triangles()
+    boxes, links = h.nodes()
+    # post-build order == the reference's std::sort sequence (compared by content: identical triangles are
+    # interchangeable, the reference itself cannot tell them apart)
+    ps = oraclelib.parsed_scene(name)
+    for k in ("v", "vn", "vt"):
+        assert np.array_equal(bits(ps[k][tr["face"]]), bits(ps[k][g["face"]])), k
+    assert np.array_equal(ps["mtl"][tr["face"]], ps["mtl"][g["face"]])
+    assert np.array_equal(bits(tr["normal"]), bits(g["normal"]))
+    assert np.array_equal(bits(boxes), bits(g["node_box"])) and np.array_equal(links, g["node_link"])
+    cam = h.camera()
+    assert np.array_equal(bits(np.concatenate([cam["eye"], cam["llc"], cam["horizontal"], cam["vertical"]])), bits(g["camera"]))
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_host_build_matches_oracle(name, host_scenes, oracle_scenes):
+    h, o = host_scenes[name], oracle_scenes[name]
+    tr = h.triangles()
+    assert np.array_equal(tr["face"], o.order())
+    d = o.derived()
+    assert np.array_equal(bits(tr["normal"]), bits(d["normal"]))
+    ob, ol = o.nodes()
+    hb, hl = h.nodes()
+    assert np.array_equal(bits(hb), bits(ob)) and np.array_equal(hl, ol)
+    assert np.array_equal(bits(np.concatenate(list(h.camera()[k] for k in ("eye", "llc", "horizontal", "vertical")))), bits(o.camera()))
+    # lights: cumulative areas in OBJ order
+    ls, lv, lvn, cum = h.lights()
+    ps = o.ps
+    names = h.material_names()
+    for l, (mi, rad) in zip(ls, ps["lights"]):
+        assert names[l["material"]] == ps["materials"][mi]["name"]
+        mat = h.materials()[l["material"]]
+        assert mat["is_emissive"] == 1 and np.allclose(mat["radiance"], rad, rtol=0, atol=0)
+        sel = np.flatnonzero(ps["mtl"] == mi)
+        assert l["n_tris"] == len(sel)
+        assert np.array_equal(bits(lv[l["first_tri"]:l["first_tri"] + l["n_tris"]]), bits(ps["v"][sel]))
+        seg = cum[l["first_tri"]:l["first_tri"] + l["n_tris"]]
+        assert np.all(np.diff(seg) >= 0) and seg[-1] == mat["area"]
+        assert np.array_equal(seg, d["area"][np.isin(tr["face"], sel)][np.argsort(tr["face"][np.isin(tr["face"], sel)])])
+
+
+def test_textures_loaded(host_scenes):
+    tex = host_scenes["staircase"].textures()
+    assert sorted(t.shape for t in tex) == sorted([(894, 894, 3), (512, 512, 3), (1200, 1600, 3)])
+    mats = {n: m for n, m in zip(host_scenes["staircase"].material_names(), host_scenes["staircase"].materials())}
+    assert mats["Wood"]["texture"] >= 0 and mats["Glass"]["texture"] == -1 and abs(mats["Glass"]["Ni"] - 1.5) < 1e-7
+
+
+def write(path, text):
+    with open(path, "w") as f:
+        f.write(text)
+
+
+def test_loader_quirks(tmp_path):
+    """Behaviours of the reference's hand-rolled loaders that scenes rely on."""
+    d = str(tmp_path)
+    write(d + "/q.xml", '<?xml version="1.0"?>\n<!-- c -->\n<camera type="perspective" width="32" height="16" fovy="40.5">\n'
+          ' <eye x="0" y="1" z="-5"/> <lookat x="0" y="1" z="0"/> <up x="0" y="1" z="0"/>\n</camera>\n'
+          '<light mtlname="L" radiance="1.5,\n    2.5,\n  3.5"/>\n<other/>\n<light mtlname="M" radiance="4, 5"/>\n')
+    # vn before the first vt -> slots are read v/vn/vt (isvnvt); a quad: only the first three corners are used
+    write(d + "/q.obj", "v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvn 0 0 -1\nvn 0 0 1\nvt 0.25 0.75\nvt 0.5 0.5\n"
+          "usemtl A\nf 1/1/2 2/1/2 3/1/2 4/1/2\nusemtl L\nf 1/2/1 3/2/1 4/2/1\nf 1/2/1 2/2/1 3/2/1\n")
+    write(d + "/q.mtl", "newmtl A\nKd 0.1 0.2 0.3\nKs 0.4 0.5 0.6\nKt 0.9 0.9 0.9\nNs 12\nNi 1.25\nillum 2\nnewmtl L\nKd 0 0 0\nTr 0.7 0.8 0.9\n")
+    h = trt.HostScene.load(d + "/q.xml", d + "/q.obj", d + "/q.mtl", d, leaf_num=8)
+    assert h.n_tris == 3 and (h.desc.width, h.desc.height) == (32, 16)
+    names = h.material_names()
+    mats = dict(zip(names, h.materials()))
+    assert mats["L"]["radiance"] == (1.5, 2.5, 3.5) and mats["L"]["is_emissive"] == 1
+    assert mats["M"]["radiance"] == (4.0, 0.0, 5.0)  # two fields: x, then the LAST field lands in z (scene.cpp:31-49)
+    assert mats["A"]["Tr"] == (0.0, 0.0, 0.0)  # `Kt` is ignored, only `Tr` is parsed (scene.cpp:90-94)
+    assert mats["L"]["Tr"] == pytest.approx((0.7, 0.8, 0.9)) and mats["A"]["Ns"] == 12 and mats["A"]["Ni"] == 1.25
+    tr = h.triangles()
+    order = list(tr["face"])
+    a = order.index(0)
+    assert np.array_equal(tr["vn"][a].reshape(3, 3), np.tile([0, 0, -1], (3, 1)))  # slot 2 = vn index 1
+    assert np.array_equal(tr["vt"][a].reshape(3, 2), np.tile([0.5, 0.5], (3, 1)))  # slot 3 = vt index 2
+    assert np.array_equal(tr["v"][a].reshape(3, 3), [[0, 0, 0], [1, 0, 0], [1, 1, 0]])
+    # cumulative light areas: two right triangles of area 0.5
+    ls, lv, lvn, cum = h.lights()
+    assert [names[l["material"]] for l in ls] == ["L", "M"] and ls[0]["n_tris"] == 2 and ls[1]["n_tris"] == 0
+    assert cum == pytest.approx([0.5, 1.0]) and mats["L"]["area"] == pytest.approx(1.0)
+    # standard order (vt before vn): slots are v/vt/vn
+    write(d + "/s.obj", "v 0 0 0\nv 1 0 0\nv 1 1 0\nvt 0.25 0.75\nvt 0.5 0.5\nvn 0 0 -1\nvn 0 0 1\nusemtl A\nf 1/2/1 2/2/1 3/2/1\n")
+    h2 = trt.HostScene.load(d + "/q.xml", d + "/s.obj", d + "/q.mtl", d)
+    t2 = h2.triangles()
+    assert np.array_equal(t2["vt"][0].reshape(3, 2), np.tile([0.5, 0.5], (3, 1))) and np.array_equal(t2["vn"][0][:3], [0, 0, -1])
+
+
+def test_loader_errors_are_reported(tmp_path):
+    d = str(tmp_path)
+    write(d + "/q.xml", '<camera width="8" height="8" fovy="40"><eye x="0" y="0" z="0"/><lookat x="0" y="0" z="1"/><up x="0" y="1" z="0"/></camera>')
+    write(d + "/bad.obj", "v 0 0 0\nf 1/1/1 2/1/1 3/1/1\n")
+    write(d + "/q.mtl", "newmtl A\n")
+    with pytest.raises(trt.TrtError):
+        trt.HostScene.load(d + "/q.xml", d + "/bad.obj", d + "/q.mtl", d)
+    with pytest.raises(trt.TrtError):
+        trt.HostScene.load(d + "/q.xml", d + "/missing.obj", d + "/q.mtl", d)
+
+
+@pytest.mark.parametrize("nq", (9, 40))
+def test_from_arrays_matches_oracle_build(nq):
+    """Synthetic meshes (BASELINE config 5) enter through trt_host_scene_from_arrays: same derived fields and the
+    same topology as the oracle's restatement of scene.cpp:196-205 + bvh.cpp:16-144."""
+    from tinyraytracing_b200 import workloads
+
+    m = workloads.stress_mesh(nq)
+    cam = m["camera"]
+    h = trt.HostScene.from_arrays(m["v9"], m["mtl"], m["materials"], m["lights"], cam["eye"], cam["lookat"], cam["up"],
+                                  cam["fovy"], 64, 36, vn9=m["vn9"])
+    ps = dict(v=m["v9"], vn=m["vn9"], vt=np.zeros((len(m["v9"]), 6), np.float32), mtl=m["mtl"],
+              materials=[dict(m_, name=str(i)) for i, m_ in enumerate(m["materials"])], lights=m["lights"], textures=[],
+              eye=np.array(cam["eye"], np.float32), lookat=np.array(cam["lookat"], np.float32),
+              up=np.array(cam["up"], np.float32), fovy=np.float32(cam["fovy"]), width=64, height=36)
+    o = oraclelib.OracleScene(ps)
+    assert np.array_equal(h.triangles()["face"], o.order())
+    hb, hl = h.nodes()
+    ob, ol = o.nodes()
+    assert np.array_equal(bits(hb), bits(ob)) and np.array_equal(hl, ol)
+    assert np.array_equal(bits(h.triangles()["normal"]), bits(o.derived()["normal"]))
+
+
+def test_png_writer_roundtrip(tmp_path):
+    import cv2
+
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    p = str(tmp_path / "x.png")
+    assert trt.load_library().trt_write_png(p.encode(), 53, 37, img.ctypes.data, 0) == 0
+    back = cv2.imread(p, cv2.IMREAD_COLOR)
+    assert np.array_equal(back[:, :, ::-1], img)
+    big = rng.integers(0, 256, (300, 300, 3), dtype=np.uint8)  # > 64 KiB: several stored deflate blocks
+    assert trt.load_library().trt_write_png(p.encode(), 300, 300, big.ctypes.data, 0) == 0
+    assert np.array_equal(cv2.imread(p, cv2.IMREAD_COLOR)[:, :, ::-1], big)

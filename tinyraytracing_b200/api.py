@@ -59,7 +59,7 @@ class Stats(C.Structure):
 
 # every symbol include/trt.h and include/trt_host.h declare (tests check the library exports all of them)
 EXPORTS = ["trt_device_count", "trt_scene_create", "trt_scene_destroy", "trt_host_alloc", "trt_host_free",
-           "trt_trace_closest", "trt_trace_closest_async", "trt_hit_attributes", "trt_render",
+           "trt_trace_closest", "trt_trace_closest_async", "trt_trace_counters", "trt_hit_attributes", "trt_render",
            "trt_render_accumulate", "trt_resolve", "trt_get_stats", "trt_reset_stats", "trt_last_error",
            "trt_version", "trt_host_scene_load", "trt_host_scene_from_arrays", "trt_host_scene_desc",
            "trt_host_scene_faces", "trt_host_scene_material_name", "trt_host_scene_build_seconds",
@@ -95,6 +95,7 @@ def load_library():
     L.trt_trace_closest.argtypes = [vp, vp, sz, vp, vp, u32]
     L.trt_trace_closest_async.argtypes = [vp, vp, sz, vp, vp, u32, vp]
     L.trt_hit_attributes.argtypes = [vp, vp, vp, vp, sz, vp, vp]
+    L.trt_trace_counters.argtypes = [vp, vp, sz, vp]
     L.trt_render.argtypes = [vp, C.POINTER(RenderParams), vp]
     L.trt_render_accumulate.argtypes = [vp, C.POINTER(RenderParams), vp, vp]
     L.trt_resolve.argtypes = [vp, vp, i32, vp, vp, vp]
@@ -264,6 +265,13 @@ class DeviceScene:
     def trace_closest_async(self, d_rays_ptr, n, d_id_ptr, d_t_ptr, flags=0, stream=0):
         _check(self.lib.trt_trace_closest_async(self.h, d_rays_ptr, n, d_id_ptr, d_t_ptr, flags, stream),
                "trt_trace_closest_async")
+
+    def trace_counters(self, rays):
+        """Per-ray averages of the default traversal's work: wide nodes, box tests, leaves, leaf triangles."""
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        out = np.zeros(4, np.uint64)
+        _check(self.lib.trt_trace_counters(self.h, rays.ctypes.data, len(rays), out.ctypes.data), "trt_trace_counters")
+        return dict(zip(("nodes", "boxes", "leaves", "tris"), (out / max(len(rays), 1)).tolist()))
 
     def hit_attributes(self, rays, ids, t):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)

@@ -25,6 +25,21 @@ struct __align__(16) RefNode
     int4 d;
 };
 
+// ---- fast layout: 4-wide BVH whose primitives are the reference's LEAVES (bvh.cpp:43-48), 128 B per node ----
+// Child k's box is (lox[k] loy[k] loz[k]) - (hix[k] hiy[k] hiz[k]).  A leaf child carries the reference leaf's
+// own padded box bit for bit (so its slab test IS the reference's interactAABB on that leaf); an inner child's
+// box is the exact float union of the leaf boxes below it.  link >= 0: wide node index; link < 0: reference
+// leaf, ~link = first<<3 | (num-1); TRT_LINK_EMPTY: unused slot.
+#define TRT_LINK_EMPTY 0x7fffffff
+#define TRT_LINK_EXIT ((int32_t)0x80000000)
+#define TRT_WIDE_STACK 64
+struct __align__(16) WideNode
+{
+    float4 lox, loy, loz, hix, hiy, hiz;
+    int4 link;
+    int4 pad;
+};
+
 // Triangle for the intersection test (48 B): (p1.xyz N.x) (p2.xyz N.y) (p3.xyz N.z)
 struct __align__(16) TriGeom
 {
@@ -70,6 +85,10 @@ struct SceneView
     // reference-topology layout
     const RefNode *ref_nodes;
     int32_t root_link; // link of the root (leaf link when the whole scene is one leaf); 0x7fffffff = empty scene
+    // fast layout (wide_root: node 0, or a leaf link when the scene is a single leaf, or TRT_LINK_EMPTY)
+    const WideNode *wide_nodes;
+    int32_t wide_root;
+    int32_t use_wide; // 0: the scene has no wide layout (too deep for its stack): reference-topology kernels only
     int32_t n_tris;
     const TriGeom *tri_geom; // post-build order
     const uint32_t *tri_key; // tie key, higher wins at equal t
@@ -92,8 +111,14 @@ struct AccelBuild
     std::vector<TriGeom> tri_geom;
     std::vector<uint32_t> tri_key;
     int32_t n_leaves = 0, ref_depth = 0;
+    std::vector<WideNode> wide_nodes;
+    int32_t wide_root = TRT_LINK_EMPTY, wide_depth = 0;
+    double sah_ref = 0, sah_wide = 0; // expected box tests per random ray (surface-area heuristic), for the log
 };
 
 // Builds the layouts from the reference topology in `desc`. Returns "" or an error text.
 std::string buildAccel(const trt_scene_desc &desc, AccelBuild &out);
+// Builds the 4-wide fast layout over the reference leaves into `out` (after buildAccel). A non-empty return
+// means the layout is unavailable for this scene (the reference-topology kernels are used instead).
+std::string buildWide(const trt_scene_desc &desc, AccelBuild &out);
 } // namespace trt

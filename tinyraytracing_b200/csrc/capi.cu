@@ -162,6 +162,11 @@ int trt_scene_create(const trt_scene_desc *desc, int device, trt_scene **out)
         return rc;
     v.root_link = ab.root_link;
     v.n_tris = desc->n_tris;
+    const std::string wide_err = buildWide(*desc, ab);
+    v.use_wide = wide_err.empty() ? 1 : 0;
+    v.wide_root = ab.wide_root;
+    if ((rc = upload(s.get(), ab.wide_nodes.data(), ab.wide_nodes.size(), &v.wide_nodes)))
+        return rc;
 
     std::vector<TriShade> shade(desc->n_tris);
     for (int i = 0; i < desc->n_tris; ++i)
@@ -237,7 +242,7 @@ int trt_scene_create(const trt_scene_desc *desc, int device, trt_scene **out)
     v.cam.width = desc->width, v.cam.height = desc->height;
     s->width = desc->width, s->height = desc->height;
 
-    s->stats.accel_nodes = (int32_t)ab.ref_nodes.size();
+    s->stats.accel_nodes = (int32_t)(v.use_wide ? ab.wide_nodes.size() : ab.ref_nodes.size());
     s->stats.accel_leaves = ab.n_leaves;
     s->stats.ref_depth = ab.ref_depth;
     s->stats.device = device;
@@ -402,6 +407,33 @@ int trt_hit_attributes(trt_scene *s, const float *rays6, const int32_t *tri_id, 
     cleanup();
     return rc;
 #undef TRT_TRY
+}
+
+int trt_trace_counters(trt_scene *s, const float *rays6, size_t n, uint64_t out4[4])
+{
+    if (!s || !out4 || (!rays6 && n))
+        return fail(TRT_ERR_INVALID, "trt_trace_counters: null argument");
+    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    if (n == 0)
+        return TRT_OK;
+    TRT_CUDA(cudaSetDevice(s->device));
+    float *d_r = nullptr;
+    unsigned long long *d_o = nullptr;
+    TRT_CUDA(cudaMalloc((void **)&d_r, n * 24));
+    if (cudaMalloc((void **)&d_o, 32) != cudaSuccess)
+    {
+        cudaFree(d_r);
+        return fail(TRT_ERR_CUDA, "cudaMalloc failed");
+    }
+    cudaMemcpyAsync(d_r, rays6, n * 24, cudaMemcpyHostToDevice, s->stream);
+    cudaMemsetAsync(d_o, 0, 32, s->stream);
+    int rc = launchClosestCounters(s, d_r, n, d_o, s->stream);
+    cudaMemcpyAsync(out4, d_o, 32, cudaMemcpyDeviceToHost, s->stream);
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_r), cudaFree(d_o);
+    if (rc == TRT_OK && e != cudaSuccess)
+        return fail(TRT_ERR_CUDA, std::string("trt_trace_counters: ") + cudaGetErrorString(e));
+    return rc;
 }
 
 int trt_render_accumulate(trt_scene *s, const trt_render_params *p, double *d_accum, void *stream)

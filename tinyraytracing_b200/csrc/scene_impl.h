@@ -49,6 +49,7 @@ namespace trt
 // trace.cu
 int launchClosest(trt_scene *s, const float *d_rays6, size_t n, int32_t *d_id, float *d_t, uint32_t flags,
                   cudaStream_t stream);
+int launchClosestCounters(trt_scene *s, const float *d_rays6, size_t n, unsigned long long *d_out4, cudaStream_t stream);
 int launchHitAttributes(trt_scene *s, const float *d_rays6, const int32_t *d_id, const float *d_t, size_t n,
                         float *d_hitp3, float *d_pn3, cudaStream_t stream);
 // wavefront.cu

@@ -18,7 +18,7 @@ __device__ __forceinline__ void loadRay(const float *rays6, size_t i, float3 &S,
     d = f3(b.y, c.x, c.y);
 }
 
-template <int MODE> // 0: ordered + pruned reference topology, 1: exhaustive reference walk
+template <int MODE> // 0: ordered + pruned reference topology, 1: exhaustive reference walk, 2: fast layout
 __global__ void __launch_bounds__(kTraceBlock) k_closest(SceneView sv, const float *__restrict__ rays6, size_t n,
                                                          int32_t *__restrict__ out_id, float *__restrict__ out_t)
 {
@@ -30,12 +30,40 @@ __global__ void __launch_bounds__(kTraceBlock) k_closest(SceneView sv, const flo
     Hit hit;
     if (MODE == 1)
         traceRefTopology<true>(sv, S, d, hit);
-    else
+    else if (MODE == 0)
         traceRefTopology<false>(sv, S, d, hit);
+    else
+        traceClosest(sv, S, d, hit);
     if (out_id)
         out_id[i] = hit.id;
     if (out_t)
         out_t[i] = hit.t;
+}
+
+// Work counters of the fast layout's walk (design evaluation / reporting): sums over the batch.
+__global__ void __launch_bounds__(kTraceBlock) k_closest_counters(SceneView sv, const float *__restrict__ rays6, size_t n,
+                                                                  unsigned long long *__restrict__ out4)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    TraceCounters c{0, 0, 0, 0};
+    if (i < n)
+    {
+        float3 S, d;
+        loadRay(rays6, i, S, d);
+        Hit hit;
+        if (!needsStrictWalk(S, d))
+            traceWide<true>(sv, S, d, hit, &c);
+    }
+    uint32_t v[4] = {c.nodes, c.boxes, c.leaves, c.tris};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        uint32_t x = v[k];
+        for (int o = 16; o > 0; o >>= 1)
+            x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0 && x)
+            atomicAdd(out4 + k, (unsigned long long)x);
+    }
 }
 
 __global__ void __launch_bounds__(128) k_hit_attributes(SceneView sv, const float *__restrict__ rays6,
@@ -71,11 +99,22 @@ int launchClosest(trt_scene *s, const float *d_rays6, size_t n, int32_t *d_id, f
     const unsigned grid = (unsigned)((n + kTraceBlock - 1) / kTraceBlock);
     if (flags & TRT_TRACE_EXHAUSTIVE)
         k_closest<1><<<grid, kTraceBlock, 0, stream>>>(s->view, d_rays6, n, d_id, d_t);
-    else
+    else if (flags & TRT_TRACE_REFTOPO)
         k_closest<0><<<grid, kTraceBlock, 0, stream>>>(s->view, d_rays6, n, d_id, d_t);
+    else
+        k_closest<2><<<grid, kTraceBlock, 0, stream>>>(s->view, d_rays6, n, d_id, d_t);
     TRT_CUDA(cudaGetLastError());
     s->stats.kernel_launches++;
     s->stats.rays_closest += n;
+    return TRT_OK;
+}
+
+int launchClosestCounters(trt_scene *s, const float *d_rays6, size_t n, unsigned long long *d_out4, cudaStream_t stream)
+{
+    if (n == 0 || !s->view.use_wide)
+        return TRT_OK;
+    k_closest_counters<<<(unsigned)((n + kTraceBlock - 1) / kTraceBlock), kTraceBlock, 0, stream>>>(s->view, d_rays6, n, d_out4);
+    TRT_CUDA(cudaGetLastError());
     return TRT_OK;
 }
 

@@ -154,4 +154,126 @@ __device__ __forceinline__ void traceRefTopology(const SceneView &sv, float3 S, 
         }
     }
 }
+
+// ---- fast layout -------------------------------------------------------------------------------------------
+// Rays for which the slab test is not monotone in the box (a direction component that is exactly +-0 gives
+// inf*0 = NaN; non-finite origins / directions) take the reference's own exhaustive walk.
+__device__ __forceinline__ bool needsStrictWalk(float3 S, float3 d)
+{
+    // 1/d overflows to +-inf for zero AND for denormal components: test the reciprocal itself
+    const float3 inv = rcpDir(d);
+    const bool inf_rcp = !(fabsf(inv.x) <= 3.4028235e38f) || !(fabsf(inv.y) <= 3.4028235e38f) || !(fabsf(inv.z) <= 3.4028235e38f);
+    const float sum = ((S.x + S.y) + S.z) + ((d.x + d.y) + d.z); // inf or NaN anywhere -> not finite
+    return inf_rcp || !(fabsf(sum) < 3.0e38f);
+}
+
+struct TraceCounters
+{
+    uint32_t nodes, boxes, leaves, tris;
+};
+
+// Slab test of one child of a wide node: the reference's arithmetic ((B - S) * inv, un-fused).  For rays
+// admitted here every operand is finite and inv is finite and non-zero, so no NaN can appear and IEEE
+// fminf / fmaxf (one instruction) equal glm's compare-select min / max.
+__device__ __forceinline__ bool childPass(float3 S, float3 inv, float ax, float ay, float az, float bx, float by, float bz,
+                                          float &t0)
+{
+    const float inx = (bx - S.x) * inv.x, iny = (by - S.y) * inv.y, inz = (bz - S.z) * inv.z;
+    const float outx = (ax - S.x) * inv.x, outy = (ay - S.y) * inv.y, outz = (az - S.z) * inv.z;
+    const float t1 = fminf(fmaxf(inx, outx), fminf(fmaxf(iny, outy), fmaxf(inz, outz)));
+    t0 = fmaxf(fminf(inx, outx), fmaxf(fminf(iny, outy), fminf(inz, outz)));
+    return (t1 >= t0) && (((t0 > 0.0f) ? t0 : t1) > 0.0f);
+}
+
+// 4-wide walk over the reference leaves: while-while (inner nodes until a leaf is reached, then the leaf scan),
+// nearest child first, entry-distance pruning at push and at pop.
+template <bool STATS>
+__device__ __forceinline__ void traceWide(const SceneView &sv, float3 S, float3 d, Hit &hit, TraceCounters *cnt)
+{
+    hit.t = TRT_INF, hit.id = -1, hit.key = 0xFFFFFFFFu;
+    if (sv.wide_root == TRT_LINK_EMPTY)
+        return;
+    const float3 inv = rcpDir(d);
+    int32_t stack_link[TRT_WIDE_STACK];
+    float stack_t[TRT_WIDE_STACK];
+    stack_link[0] = TRT_LINK_EXIT;
+    stack_t[0] = -1.f;
+    int sp = 1;
+    int32_t cur = sv.wide_root;
+    for (;;)
+    {
+        while (cur >= 0)
+        {
+            const float4 *np = reinterpret_cast<const float4 *>(sv.wide_nodes + cur);
+            const float4 lox = __ldg(np), loy = __ldg(np + 1), loz = __ldg(np + 2);
+            const float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
+            const int4 lk = __ldg(reinterpret_cast<const int4 *>(np + 6));
+            float t0, t1, t2, t3;
+            bool h0 = childPass(S, inv, lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, t0);
+            bool h1 = childPass(S, inv, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, t1);
+            bool h2 = (lk.z != TRT_LINK_EMPTY) && childPass(S, inv, lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, t2);
+            bool h3 = (lk.w != TRT_LINK_EMPTY) && childPass(S, inv, lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, t3);
+            if (STATS)
+                cnt->nodes++, cnt->boxes += 2 + (lk.z != TRT_LINK_EMPTY) + (lk.w != TRT_LINK_EMPTY);
+            h0 = h0 && !(t0 > hit.t);
+            h1 = h1 && !(t1 > hit.t);
+            h2 = h2 && !(t2 > hit.t);
+            h3 = h3 && !(t3 > hit.t);
+            // nearest hit child continues, the others are pushed (far ones first would need a full sort; the
+            // pop-time distance check prunes them anyway)
+            float tn = 3.0e38f;
+            int32_t next = TRT_LINK_EMPTY;
+            if (h0)
+                tn = t0, next = lk.x;
+            if (h1 && t1 < tn)
+                tn = t1, next = lk.y;
+            if (h2 && t2 < tn)
+                tn = t2, next = lk.z;
+            if (h3 && t3 < tn)
+                tn = t3, next = lk.w;
+            if (next == TRT_LINK_EMPTY)
+            {
+                // nothing hit: pop
+                do
+                {
+                    --sp;
+                    cur = stack_link[sp];
+                } while (stack_t[sp] > hit.t);
+                continue;
+            }
+            if (h0 && lk.x != next)
+                stack_link[sp] = lk.x, stack_t[sp] = t0, ++sp;
+            if (h1 && lk.y != next)
+                stack_link[sp] = lk.y, stack_t[sp] = t1, ++sp;
+            if (h2 && lk.z != next)
+                stack_link[sp] = lk.z, stack_t[sp] = t2, ++sp;
+            if (h3 && lk.w != next)
+                stack_link[sp] = lk.w, stack_t[sp] = t3, ++sp;
+            cur = next;
+        }
+        if (cur == TRT_LINK_EXIT)
+            return;
+        const int leaf = ~cur;
+        if (STATS)
+            cnt->leaves++, cnt->tris += (leaf & 7) + 1;
+        scanLeaf(sv, leaf >> 3, (leaf & 7) + 1, S, d, hit);
+        do
+        {
+            --sp;
+            cur = stack_link[sp];
+        } while (stack_t[sp] > hit.t);
+    }
+}
+
+// Closest hit with the default (fast) layout; falls back to the reference topology for strict rays and for
+// scenes without a wide layout.
+__device__ __forceinline__ void traceClosest(const SceneView &sv, float3 S, float3 d, Hit &hit)
+{
+    if (!sv.use_wide)
+        traceRefTopology<false>(sv, S, d, hit);
+    else if (needsStrictWalk(S, d))
+        traceRefTopology<true>(sv, S, d, hit);
+    else
+        traceWide<false>(sv, S, d, hit, nullptr);
+}
 } // namespace trt

@@ -132,7 +132,10 @@ __global__ void __launch_bounds__(kBlock) k_raygen(SceneView sv, WfBuffers wf, i
 template <bool REFTOPO>
 __device__ __forceinline__ void traceAny(const SceneView &sv, float3 S, float3 d, Hit &hit)
 {
-    traceRefTopology<false>(sv, S, d, hit);
+    if (REFTOPO)
+        traceRefTopology<false>(sv, S, d, hit);
+    else
+        traceClosest(sv, S, d, hit);
 }
 
 template <bool REFTOPO>

@@ -116,6 +116,7 @@ void trt_host_free(void *p);
 #define TRT_TRACE_EXHAUSTIVE 2u  /* walk the reference topology with the reference's visiting rule
                                     (no ordering, no pruning: bvh.cpp:156-174) — validation mode     */
 #define TRT_TRACE_REFTOPO 4u     /* ordered + pruned walk of the reference binary topology          */
+#define TRT_TRACE_PLAIN 8u       /* fast layout, one thread per ray without the persistent ray pool  */
 
 /* rays6: n*(origin.xyz, direction.xyz) float32.  tri_id: post-build triangle index of the reference's
  * winner (tie rule of bvh.cpp:168-172,219), -1 on miss.  t: HitRecord::distance, TRT_INF on miss.
@@ -151,6 +152,7 @@ typedef struct trt_render_params {
 } trt_render_params;
 
 #define TRT_RENDER_REFTOPO 1u /* trace with the reference-topology kernel instead of the fast layout */
+#define TRT_RENDER_PLAIN 2u   /* fast layout, plain thread-per-ray traversal instead of the persistent walker */
 
 /* Renders the sample range and writes the reference's image buffer: double[H*W*3], row-major RGB, rows
  * top to bottom, already divided by spp (main.cpp:74,101-108) — what imshow (main.cpp:19-42) consumes. */

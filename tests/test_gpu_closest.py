@@ -8,7 +8,7 @@ from conftest import SCENES, make_rays
 
 pytestmark = pytest.mark.gpu
 
-MODES = {"default": 0, "reftopo": trt.TRACE_REFTOPO, "exhaustive": trt.TRACE_EXHAUSTIVE}
+MODES = {"default": 0, "plain": trt.TRACE_PLAIN, "reftopo": trt.TRACE_REFTOPO, "exhaustive": trt.TRACE_EXHAUSTIVE}
 
 
 @pytest.mark.parametrize("name", SCENES)
@@ -21,6 +21,25 @@ def test_closest_hit_bit_exact(name, mode, host_scenes, oracle_scenes, device_sc
     assert len(bad) == 0, "%d id mismatches, first ray %d gpu %d oracle %d" % (len(bad), bad[0], ids[bad[0]], oid[bad[0]])
     assert np.array_equal(t.view(np.uint32), ot.view(np.uint32))
     assert (ids >= 0).sum() > len(rays) // 4  # the batch really hits geometry
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_gpu_reproduces_reference_golden(name, device_scenes):
+    """Closest hits of the UNMODIFIED reference (tests/golden, tools/make_golden.py): distance bits, triangle
+    identity (by content: identical triangles are one identity in the reference's HitRecord), hit point, pn."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + "_closest.npz"))
+    dev = device_scenes[name]
+    for flags in MODES.values():
+        ids, t = dev.trace_closest(g["rays"], flags)
+        assert np.array_equal(t.view(np.uint32), g["t"].view(np.uint32))
+        assert np.array_equal(np.where(ids >= 0, g["canon"][np.maximum(ids, 0)], -1), g["id"])
+    hp, pn = dev.hit_attributes(g["rays"], ids, t)
+    hit = ids >= 0
+    assert np.array_equal(hp[hit].view(np.uint32), g["hitpoint"][hit].view(np.uint32))
+    ok = np.isfinite(g["pn"][hit]).all(axis=1)
+    assert np.abs(pn[hit][ok] - g["pn"][hit][ok]).max() <= 1e-6
 
 
 @pytest.mark.parametrize("name", SCENES)
@@ -63,7 +82,7 @@ def test_edge_cases(host_scenes, oracle_scenes, device_scenes):
     special[2000:2100, 3:] = 0.0       # zero direction
     special[2100:2200, 3:] = np.nan    # NaN direction (normalize of a zero vector in the reference)
     special[2200:2300, :3] = np.inf    # garbage origin
-    for flags in (0, trt.TRACE_REFTOPO, trt.TRACE_EXHAUSTIVE):
+    for flags in MODES.values():
         ids, t = dev.trace_closest(special, flags)
         oid, ot = orc.trace(special)
         assert np.array_equal(ids, oid)

@@ -79,3 +79,24 @@ def test_ray_counts(oracle_scenes, device_scenes):
     assert abs(int(st["rays_closest"]) - int(closest)) <= 0.005 * closest
     # shadow rays: the GPU skips light samples behind the surface (dot(wo, pn) <= 0), the reference traces them
     assert 0 < st["rays_shadow"] <= shadow
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_render_agrees_with_reference_statistically(name, device_scenes):
+    """Against the reference's own shade() (tests/golden/<scene>_render.npz, two independent 64-spp runs A1, A2
+    made by tools/make_golden.py): the reference is only statistically reproducible, so this is the
+    noise-floor test of SURVEY §8c-3 on radiance clipped at 4x the image mean (NEE 1/r^2 fireflies dominate the
+    raw RMSE): channel means within 5 % (+ the A1/A2 spread) and RMSE(GPU, A) <= 1.25 * RMSE(A1, A2)."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + "_render.npz"))
+    a1, a2, spp = g["run1"].astype(np.float64), g["run2"].astype(np.float64), int(g["spp"])
+    img = device_scenes[name].render(spp, seed=4321)
+    clip = 4 * a1.mean()
+    c1, c2, cg = (np.minimum(x, clip) for x in (a1, a2, img))
+    m1, m2, mg = (x.mean(axis=(0, 1)) for x in (c1, c2, cg))
+    ref_mean = 0.5 * (m1 + m2)
+    assert np.all(np.abs(mg - ref_mean) <= 0.05 * ref_mean + np.abs(m1 - m2)), (mg, m1, m2)
+    floor = np.sqrt(((c1 - c2) ** 2).mean())
+    assert np.sqrt(((cg - c1) ** 2).mean()) <= 1.25 * floor
+    assert np.sqrt(((cg - c2) ** 2).mean()) <= 1.25 * floor

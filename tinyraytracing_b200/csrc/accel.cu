@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <functional>
 
 namespace trt
@@ -261,11 +262,36 @@ std::string buildWide(const trt_scene_desc &desc, AccelBuild &out)
         return "";
     }
     WideBuilder wb{prims, {}, {}};
-    wb.order.resize(prims.size());
-    for (size_t i = 0; i < prims.size(); ++i)
-        wb.order[i] = (int32_t)i;
-    wb.bn.reserve(prims.size() * 2);
-    wb.build(0, (int)prims.size());
+    const char *mode = getenv("TRT_WIDE_SOURCE"); // "ref": collapse the reference binary tree as it is (experiments)
+    if (mode && std::string(mode) == "ref")
+    {
+        // binary nodes = the reference's, pre-order; leaf prims in the same left-to-right order as `prims`
+        std::vector<int32_t> leafPrim(nn, -1);
+        int32_t lp = 0;
+        for (int i = 0; i < nn; ++i)
+            if (desc.node_link[(size_t)i * 4 + 3] > 0)
+                leafPrim[i] = lp++;
+        wb.bn.resize(nn);
+        for (int i = 0; i < nn; ++i)
+        {
+            const int32_t *lk = desc.node_link + (size_t)i * 4;
+            const float *b = desc.node_box + (size_t)i * 6;
+            for (int a = 0; a < 3; ++a)
+                wb.bn[i].lo[a] = b[a], wb.bn[i].hi[a] = b[3 + a];
+            if (lk[3] > 0)
+                wb.bn[i].left = leafPrim[i], wb.bn[i].right = -2;
+            else
+                wb.bn[i].left = lk[0], wb.bn[i].right = lk[1];
+        }
+    }
+    else
+    {
+        wb.order.resize(prims.size());
+        for (size_t i = 0; i < prims.size(); ++i)
+            wb.order[i] = (int32_t)i;
+        wb.bn.reserve(prims.size() * 2);
+        wb.build(0, (int)prims.size());
+    }
     const std::vector<BNode> &bn = wb.bn;
 
     // collapse: a wide node adopts grandchildren, largest surface area first, until it has 4 children

@@ -259,6 +259,7 @@ void trt_scene_destroy(trt_scene *s)
     destroyWavefront(s);
     for (void *p : s->allocations)
         cudaFree(p);
+    cudaFree(s->d_counter);
     for (int b = 0; b < 2; ++b)
     {
         if (s->stage_in[b])

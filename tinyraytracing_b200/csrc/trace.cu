@@ -3,6 +3,8 @@
 #include "traverse.cuh"
 #include "barycentric.cuh"
 
+#include <algorithm>
+
 namespace trt
 {
 namespace
@@ -38,6 +40,29 @@ __global__ void __launch_bounds__(kTraceBlock) k_closest(SceneView sv, const flo
         out_id[i] = hit.id;
     if (out_t)
         out_t[i] = hit.t;
+}
+
+struct BatchRays
+{
+    const float *rays6;
+    int32_t *out_id;
+    float *out_t;
+    __device__ __forceinline__ void load(size_t i, float3 &S, float3 &d) const { loadRay(rays6, i, S, d); }
+    __device__ __forceinline__ void store(size_t i, const Hit &h) const
+    {
+        if (out_id)
+            out_id[i] = h.id;
+        if (out_t)
+            out_t[i] = h.t;
+    }
+};
+
+__global__ void __launch_bounds__(kTraceBlock) k_closest_persistent(SceneView sv, const float *__restrict__ rays6, unsigned int n,
+                                                                    int32_t *__restrict__ out_id, float *__restrict__ out_t,
+                                                                    unsigned int *counter)
+{
+    BatchRays r{rays6, out_id, out_t};
+    walkPersistent(sv, r, n, counter);
 }
 
 // Work counters of the fast layout's walk (design evaluation / reporting): sums over the batch.
@@ -101,8 +126,20 @@ int launchClosest(trt_scene *s, const float *d_rays6, size_t n, int32_t *d_id, f
         k_closest<1><<<grid, kTraceBlock, 0, stream>>>(s->view, d_rays6, n, d_id, d_t);
     else if (flags & TRT_TRACE_REFTOPO)
         k_closest<0><<<grid, kTraceBlock, 0, stream>>>(s->view, d_rays6, n, d_id, d_t);
-    else
+    else if ((flags & TRT_TRACE_PLAIN) || n > 0xfffffff0ull)
         k_closest<2><<<grid, kTraceBlock, 0, stream>>>(s->view, d_rays6, n, d_id, d_t);
+    else
+    {
+        if (!s->d_counter)
+        {
+            TRT_CUDA(cudaMalloc((void **)&s->d_counter, 256));
+            TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->persistent_blocks_per_sm, k_closest_persistent,
+                                                                   kTraceBlock, 0));
+        }
+        TRT_CUDA(cudaMemsetAsync(s->d_counter, 0, 4, stream));
+        const unsigned pgrid = (unsigned)std::min<size_t>((size_t)s->sm_count * s->persistent_blocks_per_sm, grid);
+        k_closest_persistent<<<pgrid, kTraceBlock, 0, stream>>>(s->view, d_rays6, (unsigned int)n, d_id, d_t, s->d_counter);
+    }
     TRT_CUDA(cudaGetLastError());
     s->stats.kernel_launches++;
     s->stats.rays_closest += n;

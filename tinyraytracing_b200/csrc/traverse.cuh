@@ -47,7 +47,12 @@ __device__ __forceinline__ bool triangleHit(const TriGeom &g, float3 S, float3 d
     if (fabsf(dn) < 0.00001f)
         return false;
     const float3 p1 = f3(g.p1nx.x, g.p1nx.y, g.p1nx.z);
-    const float t = dot3(p1 - S, N) / dn;
+    const float a = dot3(p1 - S, N);
+    // opposite signs (or a == +-0 against a negative dn, ...) give t <= -0 < 0.0005: rejected by bvh.cpp:189
+    // whatever the quotient is, so the IEEE division is skipped (a NaN operand is a miss on either path)
+    if ((__float_as_int(a) ^ __float_as_int(dn)) < 0)
+        return false;
+    const float t = a / dn;
     if (t < 0.0005f)
         return false;
     if (t > best_t)
@@ -219,21 +224,26 @@ __device__ __forceinline__ void traceWide(const SceneView &sv, float3 S, float3 
             h1 = h1 && !(t1 > hit.t);
             h2 = h2 && !(t2 > hit.t);
             h3 = h3 && !(t3 > hit.t);
-            // nearest hit child continues, the others are pushed (far ones first would need a full sort; the
-            // pop-time distance check prunes them anyway)
-            float tn = 3.0e38f;
-            int32_t next = TRT_LINK_EMPTY;
-            if (h0)
-                tn = t0, next = lk.x;
-            if (h1 && t1 < tn)
-                tn = t1, next = lk.y;
-            if (h2 && t2 < tn)
-                tn = t2, next = lk.z;
-            if (h3 && t3 < tn)
-                tn = t3, next = lk.w;
-            if (next == TRT_LINK_EMPTY)
+            // order the hit children by entry distance (5-comparator network; misses sort to the end), continue
+            // with the nearest and push the rest far-to-near so that they pop near-to-far
+            float k0 = h0 ? t0 : 3.0e38f, k1 = h1 ? t1 : 3.0e38f, k2 = h2 ? t2 : 3.0e38f, k3 = h3 ? t3 : 3.0e38f;
+            int32_t l0 = lk.x, l1 = lk.y, l2 = lk.z, l3 = lk.w;
+#define TRT_CSWAP(ka, la, kb, lb)                                                                                   \
+    {                                                                                                               \
+        const bool sw = kb < ka;                                                                                    \
+        const float tk = sw ? kb : ka;                                                                              \
+        const int32_t tl = sw ? lb : la;                                                                            \
+        kb = sw ? ka : kb, lb = sw ? la : lb, ka = tk, la = tl;                                                     \
+    }
+            TRT_CSWAP(k0, l0, k1, l1)
+            TRT_CSWAP(k2, l2, k3, l3)
+            TRT_CSWAP(k0, l0, k2, l2)
+            TRT_CSWAP(k1, l1, k3, l3)
+            TRT_CSWAP(k1, l1, k2, l2)
+#undef TRT_CSWAP
+            const int nh = (int)h0 + (int)h1 + (int)h2 + (int)h3;
+            if (nh == 0)
             {
-                // nothing hit: pop
                 do
                 {
                     --sp;
@@ -241,14 +251,13 @@ __device__ __forceinline__ void traceWide(const SceneView &sv, float3 S, float3 
                 } while (stack_t[sp] > hit.t);
                 continue;
             }
-            if (h0 && lk.x != next)
-                stack_link[sp] = lk.x, stack_t[sp] = t0, ++sp;
-            if (h1 && lk.y != next)
-                stack_link[sp] = lk.y, stack_t[sp] = t1, ++sp;
-            if (h2 && lk.z != next)
-                stack_link[sp] = lk.z, stack_t[sp] = t2, ++sp;
-            if (h3 && lk.w != next)
-                stack_link[sp] = lk.w, stack_t[sp] = t3, ++sp;
+            if (nh > 3)
+                stack_link[sp] = l3, stack_t[sp] = k3, ++sp;
+            if (nh > 2)
+                stack_link[sp] = l2, stack_t[sp] = k2, ++sp;
+            if (nh > 1)
+                stack_link[sp] = l1, stack_t[sp] = k1, ++sp;
+            const int32_t next = l0;
             cur = next;
         }
         if (cur == TRT_LINK_EXIT)
@@ -262,6 +271,176 @@ __device__ __forceinline__ void traceWide(const SceneView &sv, float3 S, float3 
             --sp;
             cur = stack_link[sp];
         } while (stack_t[sp] > hit.t);
+    }
+}
+
+// ---- warp-persistent walker ---------------------------------------------------------------------------------
+// Thread-per-ray over the 4-wide layout, organised for SIMT efficiency on incoherent rays (ncu on the plain
+// while-while kernel: 7.7 of 32 lanes active, half of the loss being lanes whose ray had finished):
+//   * lanes fetch a new ray from a global counter as soon as enough lanes of the warp are idle (no tail);
+//   * the inner-node loop and the leaf loop are warp-uniform: a lane that reaches a leaf postpones it and keeps
+//     walking inner nodes until no lane of the warp still lacks a leaf, then the warp scans leaves together.
+// Results are identical to traceWide: only the order in which a ray's own nodes are visited changes, and the
+// (t, key) order decides the winner (see the header comment).
+struct WalkState
+{
+    float3 S, d, inv;
+    Hit hit;
+    int32_t cur, leaf; // cur: inner node / leaf link / TRT_LINK_EXIT; leaf: postponed leaf link or TRT_LINK_EMPTY
+    int sp;
+};
+
+#define TRT_WALK_POP(st, stack_link, stack_t)                                                                        \
+    do                                                                                                              \
+    {                                                                                                               \
+        --st.sp;                                                                                                    \
+        st.cur = stack_link[st.sp];                                                                                 \
+    } while (stack_t[st.sp] > st.hit.t)
+
+// One inner-node step of lane state `st` (st.cur >= 0 on entry).
+__device__ __forceinline__ void walkNodeStep(const SceneView &sv, WalkState &st, int32_t *stack_link, float *stack_t)
+{
+    const float4 *np = reinterpret_cast<const float4 *>(sv.wide_nodes + st.cur);
+    const float4 lox = __ldg(np), loy = __ldg(np + 1), loz = __ldg(np + 2);
+    const float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
+    const int4 lk = __ldg(reinterpret_cast<const int4 *>(np + 6));
+    float t0, t1, t2, t3;
+    bool h0 = childPass(st.S, st.inv, lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, t0);
+    bool h1 = childPass(st.S, st.inv, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, t1);
+    bool h2 = (lk.z != TRT_LINK_EMPTY) && childPass(st.S, st.inv, lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, t2);
+    bool h3 = (lk.w != TRT_LINK_EMPTY) && childPass(st.S, st.inv, lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, t3);
+    h0 = h0 && !(t0 > st.hit.t);
+    h1 = h1 && !(t1 > st.hit.t);
+    h2 = h2 && !(t2 > st.hit.t);
+    h3 = h3 && !(t3 > st.hit.t);
+    float k0 = h0 ? t0 : 3.0e38f, k1 = h1 ? t1 : 3.0e38f, k2 = h2 ? t2 : 3.0e38f, k3 = h3 ? t3 : 3.0e38f;
+    int32_t l0 = lk.x, l1 = lk.y, l2 = lk.z, l3 = lk.w;
+#define TRT_CSWAP(ka, la, kb, lb)                                                                                   \
+    {                                                                                                               \
+        const bool sw = kb < ka;                                                                                    \
+        const float tk = sw ? kb : ka;                                                                              \
+        const int32_t tl = sw ? lb : la;                                                                            \
+        kb = sw ? ka : kb, lb = sw ? la : lb, ka = tk, la = tl;                                                     \
+    }
+    TRT_CSWAP(k0, l0, k1, l1)
+    TRT_CSWAP(k2, l2, k3, l3)
+    TRT_CSWAP(k0, l0, k2, l2)
+    TRT_CSWAP(k1, l1, k3, l3)
+    TRT_CSWAP(k1, l1, k2, l2)
+#undef TRT_CSWAP
+    const int nh = (int)h0 + (int)h1 + (int)h2 + (int)h3;
+    if (nh == 0)
+    {
+        TRT_WALK_POP(st, stack_link, stack_t);
+        return;
+    }
+    if (nh > 3)
+        stack_link[st.sp] = l3, stack_t[st.sp] = k3, ++st.sp;
+    if (nh > 2)
+        stack_link[st.sp] = l2, stack_t[st.sp] = k2, ++st.sp;
+    if (nh > 1)
+        stack_link[st.sp] = l1, stack_t[st.sp] = k1, ++st.sp;
+    st.cur = l0;
+}
+
+// RAYS: struct with  __device__ bool load(size_t i, float3 &S, float3 &d)  and  void store(size_t i, const Hit &).
+// `counter` must be zero at launch; n = number of rays.  Every thread of the block must call this.
+template <typename RAYS>
+__device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, unsigned int n, unsigned int *counter)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int kRefillIdle = 8; // refill once this many lanes of the warp are idle
+    const int lane = threadIdx.x & 31;
+    int32_t stack_link[TRT_WIDE_STACK];
+    float stack_t[TRT_WIDE_STACK];
+    WalkState st;
+    unsigned int ray = 0xffffffffu; // idle
+    bool drained = false;           // the pool is empty
+    for (;;)
+    {
+        // ---- refill
+        const unsigned idle = __ballot_sync(FULL, ray == 0xffffffffu);
+        if (idle == FULL && drained)
+            return;
+        if (!drained && (__popc(idle) >= kRefillIdle))
+        {
+            unsigned int base = 0;
+            const int leader = __ffs(idle) - 1;
+            if (lane == leader)
+                base = atomicAdd(counter, (unsigned int)__popc(idle));
+            base = __shfl_sync(FULL, base, leader);
+            if (ray == 0xffffffffu)
+            {
+                const unsigned int mine = base + (unsigned int)__popc(idle & ((1u << lane) - 1u));
+                if (mine < n)
+                {
+                    ray = mine;
+                    rays.load(mine, st.S, st.d);
+                    st.hit.t = TRT_INF, st.hit.id = -1, st.hit.key = 0xFFFFFFFFu;
+                    if (!sv.use_wide || needsStrictWalk(st.S, st.d))
+                    {
+                        // rare: the reference's own walk, finished on the spot
+                        if (sv.use_wide)
+                            traceRefTopology<true>(sv, st.S, st.d, st.hit);
+                        else
+                            traceRefTopology<false>(sv, st.S, st.d, st.hit);
+                        rays.store(ray, st.hit);
+                        ray = 0xffffffffu;
+                    }
+                    else
+                    {
+                        st.inv = rcpDir(st.d);
+                        stack_link[0] = TRT_LINK_EXIT, stack_t[0] = -1.f;
+                        st.sp = 1;
+                        st.cur = sv.wide_root;
+                        st.leaf = TRT_LINK_EMPTY;
+                        if (st.cur == TRT_LINK_EMPTY) // empty scene
+                            st.cur = TRT_LINK_EXIT;
+                    }
+                }
+            }
+            if (base + (unsigned int)__popc(idle) >= n)
+                drained = true;
+        }
+        const bool live = ray != 0xffffffffu;
+        // ---- inner nodes, until no live lane still lacks a leaf
+        for (;;)
+        {
+            const bool want = live && st.cur >= 0;
+            if (!__any_sync(FULL, want && st.leaf == TRT_LINK_EMPTY))
+                break;
+            if (want)
+            {
+                walkNodeStep(sv, st, stack_link, stack_t);
+                if (st.cur < 0 && st.cur != TRT_LINK_EXIT && st.leaf == TRT_LINK_EMPTY)
+                {
+                    st.leaf = st.cur; // postpone the leaf, keep walking
+                    TRT_WALK_POP(st, stack_link, stack_t);
+                }
+            }
+        }
+        // ---- leaves
+        while (__any_sync(FULL, live && st.leaf != TRT_LINK_EMPTY))
+        {
+            if (live && st.leaf != TRT_LINK_EMPTY)
+            {
+                const int leaf = ~st.leaf;
+                scanLeaf(sv, leaf >> 3, (leaf & 7) + 1, st.S, st.d, st.hit);
+                if (st.cur < 0 && st.cur != TRT_LINK_EXIT)
+                {
+                    st.leaf = st.cur; // a second leaf was reached while the first was postponed
+                    TRT_WALK_POP(st, stack_link, stack_t);
+                }
+                else
+                    st.leaf = TRT_LINK_EMPTY;
+            }
+        }
+        // ---- finished rays
+        if (live && st.cur == TRT_LINK_EXIT && st.leaf == TRT_LINK_EMPTY)
+        {
+            rays.store(ray, st.hit);
+            ray = 0xffffffffu;
+        }
     }
 }
 

@@ -22,6 +22,9 @@
 #include "barycentric.cuh"
 
 #include <algorithm>
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace trt
 {
@@ -61,8 +64,12 @@ struct WfBuffers
     int32_t *queue[2];
     float4 *sh_o, *sh_d; // sh_o.w = contribution index (slot*n_lights + light), sh_d.w = light material
     float4 *sh_contrib;  // [slot*n_lights + light]
-    int32_t *counters;   // [0],[1]: queue sizes (ping-pong), [2]: shadow queue size
+    // [0],[1]: path queue sizes (ping-pong); [2],[3]: ray-pool cursors of the persistent trace / shadow kernels;
+    // [kShadowCount + l]: shadow rays queued for light l (segment l of sh_o / sh_d starts at l * capacity)
+    int32_t *counters;
+    int32_t capacity; // paths per batch = length of one per-light shadow segment
 };
+constexpr int kPoolTrace = 2, kPoolShadow = 3, kShadowCount = 8, kNumCounters = 8 + 32;
 
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
                                               uint32_t out[4])
@@ -124,47 +131,99 @@ __global__ void __launch_bounds__(kBlock) k_raygen(SceneView sv, WfBuffers wf, i
     {
         wf.counters[0] = n_paths;
         wf.counters[1] = 0;
-        wf.counters[2] = 0;
+        wf.counters[kPoolTrace] = 0;
     }
 }
 
 // ------------------------------------------------------------------------------------------------ K2 / K4
-template <bool REFTOPO>
-__device__ __forceinline__ void traceAny(const SceneView &sv, float3 S, float3 d, Hit &hit)
+struct QueueRays // closest-hit rays of the live paths
 {
-    if (REFTOPO)
-        traceRefTopology<false>(sv, S, d, hit);
-    else
-        traceClosest(sv, S, d, hit);
+    WfBuffers wf;
+    int qsel;
+    __device__ __forceinline__ void load(size_t i, float3 &S, float3 &d) const
+    {
+        const int slot = wf.queue[qsel][i];
+        S = xyz(wf.ray_o[slot]), d = xyz(wf.ray_d[slot]);
+    }
+    __device__ __forceinline__ void store(size_t i, const Hit &h) const
+    {
+        const int slot = wf.queue[qsel][i];
+        wf.hit_id[slot] = h.id;
+        wf.hit_t[slot] = h.t;
+    }
+};
+
+struct ShadowRays // light-sample rays, one queue segment per light (neighbouring lanes: same light, nearby pixels)
+{
+    WfBuffers wf;
+    const TriShade *tri_shade;
+    int n_lights;
+    __device__ __forceinline__ size_t locate(size_t i) const
+    {
+        int l = 0;
+        for (; l < n_lights - 1; ++l)
+        {
+            const size_t c = (size_t)wf.counters[kShadowCount + l];
+            if (i < c)
+                break;
+            i -= c;
+        }
+        return (size_t)l * wf.capacity + i;
+    }
+    __device__ __forceinline__ void load(size_t i, float3 &S, float3 &d) const
+    {
+        const size_t e = locate(i);
+        S = xyz(wf.sh_o[e]), d = xyz(wf.sh_d[e]);
+    }
+    __device__ __forceinline__ void store(size_t i, const Hit &h) const
+    {
+        const size_t e = locate(i);
+        // pathTracing.cpp:54-58: visible iff the closest hit's material is the light's material
+        const bool visible = h.id >= 0 && tri_shade[h.id].mtl == __float_as_int(wf.sh_d[e].w);
+        if (!visible)
+            wf.sh_contrib[__float_as_int(wf.sh_o[e].w)] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+};
+
+// MODE 0: warp-persistent walker over the fast layout; 1: reference topology; 2: fast layout, plain thread per ray
+template <int MODE, typename RAYS>
+__device__ __forceinline__ void traceGridStride(const SceneView &sv, RAYS &rays, unsigned int n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    {
+        float3 S, d;
+        rays.load(i, S, d);
+        Hit hit;
+        if (MODE == 1)
+            traceRefTopology<false>(sv, S, d, hit);
+        else
+            traceClosest(sv, S, d, hit);
+        rays.store(i, hit);
+    }
 }
 
-template <bool REFTOPO>
+template <int MODE>
 __global__ void __launch_bounds__(kBlock) k_trace(SceneView sv, WfBuffers wf, int qsel)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= wf.counters[qsel])
-        return;
-    const int slot = wf.queue[qsel][i];
-    const float3 S = xyz(wf.ray_o[slot]), d = xyz(wf.ray_d[slot]);
-    Hit hit;
-    traceAny<REFTOPO>(sv, S, d, hit);
-    wf.hit_id[slot] = hit.id;
-    wf.hit_t[slot] = hit.t;
+    QueueRays r{wf, qsel};
+    const unsigned int n = (unsigned int)wf.counters[qsel];
+    if (MODE != 0)
+        traceGridStride<MODE>(sv, r, n);
+    else
+        walkPersistent(sv, r, n, reinterpret_cast<unsigned int *>(wf.counters + kPoolTrace));
 }
 
-template <bool REFTOPO>
+template <int MODE>
 __global__ void __launch_bounds__(kBlock) k_shadow(SceneView sv, WfBuffers wf)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= wf.counters[2])
-        return;
-    const float4 o = wf.sh_o[i], dd = wf.sh_d[i];
-    Hit hit;
-    traceAny<REFTOPO>(sv, xyz(o), xyz(dd), hit);
-    // pathTracing.cpp:54-58: visible iff the closest hit's material is the light's material
-    const bool visible = hit.id >= 0 && sv.tri_shade[hit.id].mtl == __float_as_int(dd.w);
-    if (!visible)
-        wf.sh_contrib[__float_as_int(o.w)] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ShadowRays r{wf, sv.tri_shade, sv.n_lights};
+    unsigned int n = 0;
+    for (int l = 0; l < sv.n_lights; ++l)
+        n += (unsigned int)wf.counters[kShadowCount + l];
+    if (MODE != 0)
+        traceGridStride<MODE>(sv, r, n);
+    else
+        walkPersistent(sv, r, n, reinterpret_cast<unsigned int *>(wf.counters + kPoolShadow));
 }
 
 // ------------------------------------------------------------------------------------------------ K3
@@ -210,16 +269,20 @@ __device__ __forceinline__ void appendQueue(int32_t *counter, int32_t *queue, bo
 __global__ void __launch_bounds__(kBlock) k_shade(SceneView sv, WfBuffers wf, int qsel, int depth, int max_depth,
                                                   int sample0, uint64_t seed)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < wf.counters[qsel];
+  const int count = wf.counters[qsel];
+  // warp-uniform grid-stride loop: the queue appends below are warp-collective
+  for (int base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x)
+  {
+    const int i = base + threadIdx.x;
+    const bool active = i < count;
     bool survives = false;
     int slot = 0;
+    uint32_t mask = 0;
+    float4 weight = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active)
     {
         slot = wf.queue[qsel][i];
         const int tri = wf.hit_id[slot];
-        uint32_t mask = 0;
-        float4 weight = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 rd4 = wf.ray_d[slot];
         const int via = __float_as_int(rd4.w);
         if (tri >= 0)
@@ -310,9 +373,18 @@ __global__ void __launch_bounds__(kBlock) k_shade(SceneView sv, WfBuffers wf, in
                     const float3 contrib = intensity * brdf;
                     const int cidx = slot * sv.n_lights + li;
                     wf.sh_contrib[cidx] = xyzw(contrib, 0.f);
-                    const int sidx = atomicAdd(&wf.counters[2], 1);
-                    wf.sh_o[sidx] = xyzw(P, __int_as_float(cidx));
-                    wf.sh_d[sidx] = xyzw(wo, __int_as_float(lt.material));
+                    {
+                        // one queue segment per light, appended by the lanes that are converged here with a single
+                        // atomic: neighbouring entries are neighbouring pixels aiming at the same light
+                        cg::coalesced_group g = cg::coalesced_threads();
+                        int at = 0;
+                        if (g.thread_rank() == 0)
+                            at = atomicAdd(&wf.counters[kShadowCount + li], (int)g.size());
+                        at = g.shfl(at, 0);
+                        const size_t e = (size_t)li * wf.capacity + at + g.thread_rank();
+                        wf.sh_o[e] = xyzw(P, __int_as_float(cidx));
+                        wf.sh_d[e] = xyzw(wo, __int_as_float(lt.material));
+                    }
                     mask |= 1u << li;
                 }
 
@@ -389,14 +461,15 @@ __global__ void __launch_bounds__(kBlock) k_shade(SceneView sv, WfBuffers wf, in
         wf.weight[slot] = weight;
     }
     appendQueue(&wf.counters[qsel ^ 1], wf.queue[qsel ^ 1], survives, slot);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ K5
 __global__ void __launch_bounds__(kBlock) k_accumulate(SceneView sv, WfBuffers wf, int qsel)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= wf.counters[qsel])
-        return;
+  const int count = wf.counters[qsel];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+  {
     const int slot = wf.queue[qsel][i];
     uint32_t mask = wf.nee_mask[slot];
     float4 T = wf.thr[slot];
@@ -416,13 +489,16 @@ __global__ void __launch_bounds__(kBlock) k_accumulate(SceneView sv, WfBuffers w
     const float4 w = wf.weight[slot];
     T.x *= w.x, T.y *= w.y, T.z *= w.z;
     wf.thr[slot] = T;
+  }
 }
 
 __global__ void k_reset_counters(WfBuffers wf, int qnext)
 {
-    // before k_shade of an iteration: the queue it fills and the shadow queue start empty
-    wf.counters[qnext] = 0;
-    wf.counters[2] = 0;
+    // before k_shade of an iteration: the queue it fills, the shadow segments and the ray-pool cursors start at 0
+    if (threadIdx.x == 0)
+        wf.counters[qnext] = 0, wf.counters[kPoolTrace] = 0, wf.counters[kPoolShadow] = 0;
+    if (threadIdx.x < 32)
+        wf.counters[kShadowCount + threadIdx.x] = 0;
 }
 
 __global__ void __launch_bounds__(256) k_deposit(WfBuffers wf, double *accum, int npix, int samples_in_batch)
@@ -466,8 +542,11 @@ struct Wavefront
     int capacity = 0; // paths
     int n_lights = 0;
     std::vector<void *> allocs;
-    int32_t *h_counters = nullptr; // pinned
+    static constexpr int kRing = 8;
+    int32_t *h_ring = nullptr; // pinned: kRing snapshots of the device counters
+    cudaEvent_t ring_ev[kRing] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int blocks_trace = 1, blocks_shadow = 1;
 };
 
 void destroyWavefront(trt_scene *s)
@@ -476,8 +555,11 @@ void destroyWavefront(trt_scene *s)
         return;
     for (void *p : s->wf->allocs)
         cudaFree(p);
-    if (s->wf->h_counters)
-        cudaFreeHost(s->wf->h_counters);
+    if (s->wf->h_ring)
+        cudaFreeHost(s->wf->h_ring);
+    for (cudaEvent_t e : s->wf->ring_ev)
+        if (e)
+            cudaEventDestroy(e);
     if (s->wf->ev0)
         cudaEventDestroy(s->wf->ev0), cudaEventDestroy(s->wf->ev1);
     delete s->wf;
@@ -501,17 +583,24 @@ static int ensureWavefront(trt_scene *s, int paths)
     };
     int rc;
     WfBuffers &b = w->buf;
+    b.capacity = paths;
     if ((rc = alloc((void **)&b.ray_o, N * 16)) || (rc = alloc((void **)&b.ray_d, N * 16)) ||
         (rc = alloc((void **)&b.hit_id, N * 4)) || (rc = alloc((void **)&b.hit_t, N * 4)) ||
         (rc = alloc((void **)&b.thr, N * 16)) || (rc = alloc((void **)&b.L, N * 16)) ||
         (rc = alloc((void **)&b.weight, N * 16)) || (rc = alloc((void **)&b.nee_mask, N * 4)) ||
         (rc = alloc((void **)&b.queue[0], N * 4)) || (rc = alloc((void **)&b.queue[1], N * 4)) ||
         (rc = alloc((void **)&b.sh_o, NL * 16)) || (rc = alloc((void **)&b.sh_d, NL * 16)) ||
-        (rc = alloc((void **)&b.sh_contrib, NL * 16)) || (rc = alloc((void **)&b.counters, 16)))
+        (rc = alloc((void **)&b.sh_contrib, NL * 16)) ||
+        (rc = alloc((void **)&b.counters, kNumCounters * 4)))
         return rc;
-    TRT_CUDA(cudaMallocHost((void **)&w->h_counters, 16));
+    TRT_CUDA(cudaMemset(b.counters, 0, kNumCounters * 4));
+    TRT_CUDA(cudaMallocHost((void **)&w->h_ring, Wavefront::kRing * kNumCounters * 4));
+    for (cudaEvent_t &e : w->ring_ev)
+        TRT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     TRT_CUDA(cudaEventCreate(&w->ev0));
     TRT_CUDA(cudaEventCreate(&w->ev1));
+    TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w->blocks_trace, k_trace<0>, kBlock, 0));
+    TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w->blocks_shadow, k_shadow<0>, kBlock, 0));
     return TRT_OK;
 }
 
@@ -539,46 +628,69 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
         return rc;
     Wavefront *w = s->wf;
     const WfBuffers &b = w->buf;
-    const bool reftopo = (p.flags & TRT_RENDER_REFTOPO) != 0;
+    const int mode = (p.flags & TRT_RENDER_REFTOPO) ? 1 : ((p.flags & TRT_RENDER_PLAIN) ? 2 : 0);
+    const int nl = s->view.n_lights;
+    // The host never waits for an iteration it has just launched: every kernel reads its queue length from device
+    // memory, and the host looks at the counters of iteration it - kLag to learn when the batch has died out.
+    constexpr int kLag = 2;
+    const unsigned grid_trace = (unsigned)(s->sm_count * std::max(1, w->blocks_trace));
+    const unsigned grid_shadow = (unsigned)(s->sm_count * std::max(1, w->blocks_shadow));
+    const unsigned grid_shade = (unsigned)(s->sm_count * 8);
     TRT_CUDA(cudaEventRecord(w->ev0, stream));
     for (int s0 = p.sample_begin; s0 < p.sample_end; s0 += spb)
     {
         const int ns = std::min(spb, p.sample_end - s0);
         const int n_paths = (int)(npix * ns);
-        const unsigned grid_all = (unsigned)((n_paths + kBlock - 1) / kBlock);
-        k_raygen<<<grid_all, kBlock, 0, stream>>>(s->view, b, n_paths, s0, p.seed);
+        k_raygen<<<(unsigned)((n_paths + kBlock - 1) / kBlock), kBlock, 0, stream>>>(s->view, b, n_paths, s0, p.seed);
         s->stats.kernel_launches++;
         s->stats.paths += (uint64_t)n_paths;
-        int live = n_paths, q = 0;
-        for (int depth = 0; live > 0; ++depth)
+        s->stats.rays_closest += (uint64_t)n_paths; // iteration 0 traces every path's camera ray
+        int q = 0, consumed = 0;
+        bool dead = false;
+        auto consume = [&](int it) -> int { // counters as they stood after k_shade of iteration `it`
+            TRT_CUDA(cudaEventSynchronize(w->ring_ev[it % Wavefront::kRing]));
+            const int32_t *c = w->h_ring + (size_t)(it % Wavefront::kRing) * kNumCounters;
+            const int next_live = c[(it & 1) ^ 1];
+            uint64_t shadow = 0;
+            for (int l = 0; l < nl; ++l)
+                shadow += (uint64_t)c[kShadowCount + l];
+            s->stats.rays_shadow += shadow;
+            s->stats.rays_closest += (uint64_t)next_live; // traced by iteration it + 1
+            if (next_live == 0)
+                dead = true;
+            return TRT_OK;
+        };
+        int depth = 0;
+        for (; !dead; ++depth)
         {
-            const unsigned grid = (unsigned)((live + kBlock - 1) / kBlock);
-            if (reftopo)
-                k_trace<true><<<grid, kBlock, 0, stream>>>(s->view, b, q);
+            const unsigned grid_plain = (unsigned)(s->sm_count * 16);
+            if (mode == 1)
+                k_trace<1><<<grid_plain, kBlock, 0, stream>>>(s->view, b, q);
+            else if (mode == 2)
+                k_trace<2><<<grid_plain, kBlock, 0, stream>>>(s->view, b, q);
             else
-                k_trace<false><<<grid, kBlock, 0, stream>>>(s->view, b, q);
-            k_reset_counters<<<1, 1, 0, stream>>>(b, q ^ 1);
-            k_shade<<<grid, kBlock, 0, stream>>>(s->view, b, q, depth, p.max_depth, s0, p.seed);
-            TRT_CUDA(cudaMemcpyAsync(w->h_counters, b.counters, 12, cudaMemcpyDeviceToHost, stream));
-            TRT_CUDA(cudaStreamSynchronize(stream));
-            const int n_shadow = w->h_counters[2], next_live = w->h_counters[q ^ 1];
-            s->stats.rays_closest += (uint64_t)live;
-            s->stats.rays_shadow += (uint64_t)n_shadow;
-            s->stats.kernel_launches += 3;
-            if (n_shadow > 0)
-            {
-                const unsigned gs = (unsigned)((n_shadow + kBlock - 1) / kBlock);
-                if (reftopo)
-                    k_shadow<true><<<gs, kBlock, 0, stream>>>(s->view, b);
-                else
-                    k_shadow<false><<<gs, kBlock, 0, stream>>>(s->view, b);
-                s->stats.kernel_launches++;
-            }
-            k_accumulate<<<grid, kBlock, 0, stream>>>(s->view, b, q);
-            s->stats.kernel_launches++;
-            live = next_live;
+                k_trace<0><<<grid_trace, kBlock, 0, stream>>>(s->view, b, q);
+            k_reset_counters<<<1, 32, 0, stream>>>(b, q ^ 1);
+            k_shade<<<grid_shade, kBlock, 0, stream>>>(s->view, b, q, depth, p.max_depth, s0, p.seed);
+            TRT_CUDA(cudaMemcpyAsync(w->h_ring + (size_t)(depth % Wavefront::kRing) * kNumCounters, b.counters,
+                                     kNumCounters * 4, cudaMemcpyDeviceToHost, stream));
+            TRT_CUDA(cudaEventRecord(w->ring_ev[depth % Wavefront::kRing], stream));
+            if (mode == 1)
+                k_shadow<1><<<grid_plain, kBlock, 0, stream>>>(s->view, b);
+            else if (mode == 2)
+                k_shadow<2><<<grid_plain, kBlock, 0, stream>>>(s->view, b);
+            else
+                k_shadow<0><<<grid_shadow, kBlock, 0, stream>>>(s->view, b);
+            k_accumulate<<<grid_shade, kBlock, 0, stream>>>(s->view, b, q);
+            s->stats.kernel_launches += 5;
             q ^= 1;
+            if (depth >= kLag && (rc = consume(consumed++)))
+                return rc;
         }
+        // iterations launched after the batch died are no-ops on empty queues; drain their snapshots
+        for (; consumed < depth; ++consumed)
+            if ((rc = consume(consumed)))
+                return rc;
         k_deposit<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(b, d_accum, (int)npix, ns);
         s->stats.kernel_launches++;
         TRT_CUDA(cudaGetLastError());

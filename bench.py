@@ -51,6 +51,16 @@ def load_algorithmic_work(scene):
         return None
 
 
+def load_traffic(scene, rays_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture, per launch."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)[scene]
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) * (rays_per_launch / float(t["rays_per_launch"]))
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -288,9 +298,12 @@ def run_gpu(args):
             bytes_per_ray = 48 + 32 * A + 48 * T
             achieved = bytes_per_ray * n / (ms_res / args.steps * 1e-3) / 1e9  # per launch = per step on one GPU
             out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                               "traffic": None, "kernel": "k_closest", "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
+                               "traffic": load_traffic(SCENE, n), "kernel": "k_closest_persistent",
+                               "algorithmic_bytes_per_launch": bytes_per_ray * n, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
                                "bytes_per_ray": bytes_per_ray, "A": A, "T": T,
                                "note": "scene is L1/L2 resident (2 kB): the HBM-denominated figure is for cross-config comparison, SURVEY §8d"}
+        if not args.no_render:
+            out["render"] = render_measurements(args, tmp, rank, world, local, barrier)
         if rank == 0 and world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(f, rays)
         if args.extra and rank == 0 and world == 1:
@@ -335,6 +348,58 @@ def cpu_baseline(files, rays):
     dt = time.perf_counter() - t0
     return {"value": n / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind,
             "sample": "first %d rays of the %d-ray batch, %d OpenMP threads" % (n, len(rays), cores)}
+
+
+def render_measurements(args, tmp, rank, world, local, barrier):
+    """BASELINE configs 3 / 4: full renders, samples sharded over the ranks, ONE NCCL sum-reduce of the accumulation
+    buffers, resolve on rank 0.  spp/s = spp / (max-over-ranks device time incl. the reduce)."""
+    import torch
+    import torch.distributed as dist
+
+    import tinyraytracing_b200 as trt
+    from tinyraytracing_b200 import scenes
+    from tinyraytracing_b200.distributed import render_on_gpus
+
+    cfgs = [("config3_veach_mis", "veach-mis", 1280, 720, args.spp3)]
+    if world == 8 or args.config4:
+        cfgs.append(("config4_staircase", "staircase", 1920, 1080, args.spp4))
+    out = {}
+    for key, name, w, h, spp in cfgs:
+        f = scenes.materialize(name, os.path.join(tmp, "r_%s_%d" % (name, rank)), width=w, height=h)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)
+        try:
+            host = trt.HostScene.load(f["xml"], f["obj"], f["mtl"], f["basedir"])
+        finally:
+            os.dup2(saved, 1)
+        dev = trt.DeviceScene(host, local)
+        render_on_gpus(dev, max(world, 2), seed=1)  # warm-up: allocates the wavefront buffers, primes NCCL
+        barrier()
+        dev.reset_stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        img = render_on_gpus(dev, spp, seed=1)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        st = dev.stats()
+        counts = torch.tensor([ms, float(st["rays_closest"]), float(st["rays_shadow"]), float(st["kernel_launches"])],
+                              dtype=torch.float64, device="cuda")
+        mx = counts.clone()
+        if world > 1:
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        ms = float(mx[0].item())
+        rays = float(counts[1].item() + counts[2].item())
+        out[key] = {"scene": name, "width": w, "height": h, "spp": spp, "ms": ms, "spp_per_s": spp / (ms * 1e-3),
+                    "mrays_per_s": rays / (ms * 1e-3) / 1e6, "rays_closest": int(counts[1].item()),
+                    "rays_shadow": int(counts[2].item()), "kernel_launches": int(counts[3].item()),
+                    "image_mean": float(img.mean()) if img is not None else None,
+                    "sharding": "samples [r*spp/N, (r+1)*spp/N) per rank, scene replicated, one NCCL reduce(sum, f64, W*H*3)"}
+        dev.close()
+        barrier()
+    return out
 
 
 def extra_measurements(args, tmp):
@@ -401,6 +466,10 @@ def main():
     ap.add_argument("--flags", type=int, default=0, help="TRT_TRACE_* traversal flags (0 = default layout)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--extra", action="store_true", help="also measure the other scenes and the render path")
+    ap.add_argument("--no-render", action="store_true", help="skip the config-3/4 render measurements")
+    ap.add_argument("--config4", action="store_true", help="also render config 4 (staircase 1920x1080) when N != 8")
+    ap.add_argument("--spp3", type=int, default=256, help="spp of config 3 (veach-mis 1280x720)")
+    ap.add_argument("--spp4", type=int, default=1024, help="spp of config 4 (staircase 1920x1080)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     return run_reference(args) if args.impl == "reference" else run_gpu(args)

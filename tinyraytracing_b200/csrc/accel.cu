@@ -17,9 +17,9 @@ std::string buildAccel(const trt_scene_desc &desc, AccelBuild &out)
     for (int i = 0; i < n; ++i)
     {
         const float *v = desc.v + (size_t)i * 9, *N = desc.normal + (size_t)i * 3;
-        out.tri_geom[i].p1nx = make_float4(v[0], v[1], v[2], N[0]);
-        out.tri_geom[i].p2ny = make_float4(v[3], v[4], v[5], N[1]);
-        out.tri_geom[i].p3nz = make_float4(v[6], v[7], v[8], N[2]);
+        out.tri_geom[i].q0 = make_float4(N[0], N[1], N[2], v[0]);
+        out.tri_geom[i].q1 = make_float4(v[1], v[2], v[3], v[4]);
+        out.tri_geom[i].q2 = make_float4(v[5], v[6], v[7], v[8]);
         if (desc.mtl[i] < 0 || desc.mtl[i] >= desc.n_materials)
             return "triangle material index out of range";
     }
@@ -64,6 +64,31 @@ std::string buildAccel(const trt_scene_desc &desc, AccelBuild &out)
             out.tri_key[tri] = em ? (0x80000000u | ((uint32_t)(n_leaves - 1 - leaf_ord[i]) << 3) | (uint32_t)k)
                                   : (((uint32_t)leaf_ord[i] << 3) | (uint32_t)(7 - k));
         }
+    }
+
+    // ranks: position in descending key order with the miss key inserted
+    {
+        std::vector<int32_t> order(n);
+        for (int i = 0; i < n; ++i)
+            order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return out.tri_key[a] > out.tri_key[b]; });
+        out.tri_rank.assign(n, 0);
+        out.rank_tri.assign((size_t)n + 1, -1);
+        uint32_t r = 0;
+        bool missPlaced = false;
+        for (int i = 0; i < n; ++i)
+        {
+            if (!missPlaced && out.tri_key[order[i]] < TRT_MISS_KEY)
+            {
+                out.miss_rank = r++;
+                missPlaced = true;
+            }
+            out.tri_rank[order[i]] = r;
+            out.rank_tri[r] = order[i];
+            ++r;
+        }
+        if (!missPlaced)
+            out.miss_rank = r;
     }
 
     auto link = [&](int node) -> int32_t {

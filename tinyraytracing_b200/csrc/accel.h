@@ -32,7 +32,7 @@ struct __align__(16) RefNode
 // leaf, ~link = first<<3 | (num-1); TRT_LINK_EMPTY: unused slot.
 #define TRT_LINK_EMPTY 0x7fffffff
 #define TRT_LINK_EXIT ((int32_t)0x80000000)
-#define TRT_WIDE_STACK 64
+#define TRT_WIDE_STACK 96
 struct __align__(16) WideNode
 {
     float4 lox, loy, loz, hix, hiy, hiz;
@@ -40,10 +40,11 @@ struct __align__(16) WideNode
     int4 pad;
 };
 
-// Triangle for the intersection test (48 B): (p1.xyz N.x) (p2.xyz N.y) (p3.xyz N.z)
+// Triangle for the intersection test (48 B): q0 = (N.xyz p1.x)  q1 = (p1.y p1.z p2.x p2.y)  q2 = (p2.z p3.xyz).
+// The plane part of the test (dot(N,d), t) needs q0 and q1 only; the inside test reads q2 as well.
 struct __align__(16) TriGeom
 {
-    float4 p1nx, p2ny, p3nz;
+    float4 q0, q1, q2;
 };
 
 // Shading attributes of a triangle (fetched once per path vertex, not during traversal)
@@ -92,6 +93,11 @@ struct SceneView
     int32_t n_tris;
     const TriGeom *tri_geom; // post-build order
     const uint32_t *tri_key; // tie key, higher wins at equal t
+    // the same order as ranks (0 = highest key; the miss state has rank `miss_rank`, between the emissive and the
+    // non-emissive triangles): (t bits << 32 | rank) is then a single 64-bit key whose minimum is the winner
+    const uint32_t *tri_rank;
+    const int32_t *rank_tri; // rank -> triangle index (-1 for miss_rank)
+    uint32_t miss_rank;
     const float *tri_v;      // n*9 original vertices (barycentric solve)
     const TriShade *tri_shade;
     const DeviceMaterial *materials;
@@ -109,7 +115,9 @@ struct AccelBuild
     std::vector<RefNode> ref_nodes;
     int32_t root_link = 0x7fffffff;
     std::vector<TriGeom> tri_geom;
-    std::vector<uint32_t> tri_key;
+    std::vector<uint32_t> tri_key, tri_rank;
+    std::vector<int32_t> rank_tri;
+    uint32_t miss_rank = 0;
     int32_t n_leaves = 0, ref_depth = 0;
     std::vector<WideNode> wide_nodes;
     int32_t wide_root = TRT_LINK_EMPTY, wide_depth = 0;

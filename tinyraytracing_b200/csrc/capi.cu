@@ -160,6 +160,13 @@ int trt_scene_create(const trt_scene_desc *desc, int device, trt_scene **out)
         return rc;
     if ((rc = upload(s.get(), desc->v, (size_t)desc->n_tris * 9, &v.tri_v)))
         return rc;
+    if (ab.rank_tri.empty())
+        ab.rank_tri.assign(1, -1); // empty scene: rank 0 = miss
+    if ((rc = upload(s.get(), ab.tri_rank.data(), ab.tri_rank.size(), &v.tri_rank)))
+        return rc;
+    if ((rc = upload(s.get(), ab.rank_tri.data(), ab.rank_tri.size(), &v.rank_tri)))
+        return rc;
+    v.miss_rank = ab.miss_rank;
     v.root_link = ab.root_link;
     v.n_tris = desc->n_tris;
     const std::string wide_err = buildWide(*desc, ab);

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <deque>
+#include <future>
 #include <mutex>
 
 namespace trt
@@ -28,10 +29,24 @@ struct Ext
 };
 struct Arena
 {
-    std::deque<BVHNode> nodes; // stable addresses
+    // stable addresses; one segment per build task so that concurrent subtree builds never share a container
+    std::mutex mutex;
+    std::vector<std::unique_ptr<std::deque<BVHNode>>> segments;
+    std::deque<BVHNode> *newSegment()
+    {
+        std::lock_guard<std::mutex> g(mutex);
+        segments.emplace_back(new std::deque<BVHNode>());
+        return segments.back().get();
+    }
 };
 std::mutex g_arenaMutex;
 std::unordered_map<const BVHNode *, std::unique_ptr<Arena>> g_arenas;
+
+// Subtrees over disjoint ranges are independent once the parent's final sort has run (every later step of the
+// reference only touches its own range), so the upper levels fork one task per left child.  The sorts themselves
+// stay std::sort on one thread each: their permutation is part of the contract.
+constexpr int kForkDepth = 6;     // at most 2^6 concurrent subtree builds
+constexpr int kForkMinRange = 1 << 14;
 
 struct Builder
 {
@@ -39,14 +54,15 @@ struct Builder
     const std::vector<Ext> &ext; // per source triangle: min / max over its three vertices
     int leaf_num;
     Arena &arena;
+    std::deque<BVHNode> *segment;
     std::vector<float> pre, suf; // prefix / suffix extents, 6 floats per slot, reused across nodes
 
-    BVHNode *build(int l, int r)
+    BVHNode *build(int l, int r, int depth = 0)
     {
         if (l > r)
             return nullptr;
-        arena.nodes.emplace_back();
-        BVHNode *node = &arena.nodes.back();
+        segment->emplace_back();
+        BVHNode *node = &segment->back();
         float AA[3] = {1145141919.f, 1145141919.f, 1145141919.f}, BB[3] = {-1145141919.f, -1145141919.f, -1145141919.f};
         for (int i = l; i <= r; ++i)
         {
@@ -123,9 +139,20 @@ struct Builder
             }
         }
         sortAxis(l, r, Axis);
-        node->left = build(l, Split);
-        BVHNode *right = build(Split + 1, r);
-        node->right = right;
+        if (depth < kForkDepth && n >= kForkMinRange)
+        {
+            auto left = std::async(std::launch::async, [this, l, Split, depth] {
+                Builder sub{rec, ext, leaf_num, arena, arena.newSegment(), {}, {}};
+                return sub.build(l, Split, depth + 1);
+            });
+            node->right = build(Split + 1, r, depth + 1);
+            node->left = left.get();
+        }
+        else
+        {
+            node->left = build(l, Split, depth + 1);
+            node->right = build(Split + 1, r, depth + 1);
+        }
         return node;
     }
 
@@ -162,7 +189,7 @@ BVHNode *buildBVH(std::vector<Triangle> &triangles, int l, int r, int leaf_num)
         }
     }
     std::unique_ptr<Arena> arena(new Arena());
-    Builder b{rec, ext, leaf_num, *arena, {}, {}};
+    Builder b{rec, ext, leaf_num, *arena, arena->newSegment(), {}, {}};
     BVHNode *root = b.build(l, r);
     // apply the permutation to the fat triangles once
     std::vector<Triangle> sorted;

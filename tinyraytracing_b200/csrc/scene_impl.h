@@ -40,7 +40,7 @@ struct trt_scene
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     size_t chunk_rays = 0;
     unsigned int *d_counter = nullptr; // ray-pool counters of the persistent kernels
-    int persistent_blocks_per_sm = 1;
+    int persistent_blocks_per_sm = 1, pooled_blocks_per_sm = 1;
     trt::Wavefront *wf = nullptr;
     trt_stats stats{};
     int width = 0, height = 0;

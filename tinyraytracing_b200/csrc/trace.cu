@@ -57,12 +57,13 @@ struct BatchRays
     }
 };
 
+template <bool POOLED>
 __global__ void __launch_bounds__(kTraceBlock) k_closest_persistent(SceneView sv, const float *__restrict__ rays6, unsigned int n,
                                                                     int32_t *__restrict__ out_id, float *__restrict__ out_t,
                                                                     unsigned int *counter)
 {
     BatchRays r{rays6, out_id, out_t};
-    walkPersistent(sv, r, n, counter);
+    walkPersistent<POOLED>(sv, r, n, counter);
 }
 
 // Work counters of the fast layout's walk (design evaluation / reporting): sums over the batch.
@@ -133,12 +134,19 @@ int launchClosest(trt_scene *s, const float *d_rays6, size_t n, int32_t *d_id, f
         if (!s->d_counter)
         {
             TRT_CUDA(cudaMalloc((void **)&s->d_counter, 256));
-            TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->persistent_blocks_per_sm, k_closest_persistent,
+            TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->persistent_blocks_per_sm,
+                                                                   k_closest_persistent<false>, kTraceBlock, 0));
+            TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->pooled_blocks_per_sm, k_closest_persistent<true>,
                                                                    kTraceBlock, 0));
         }
         TRT_CUDA(cudaMemsetAsync(s->d_counter, 0, 4, stream));
-        const unsigned pgrid = (unsigned)std::min<size_t>((size_t)s->sm_count * s->persistent_blocks_per_sm, grid);
-        k_closest_persistent<<<pgrid, kTraceBlock, 0, stream>>>(s->view, d_rays6, (unsigned int)n, d_id, d_t, s->d_counter);
+        const bool pooled = (flags & TRT_TRACE_POOLED) != 0;
+        const int bps = pooled ? s->pooled_blocks_per_sm : s->persistent_blocks_per_sm;
+        const unsigned pgrid = (unsigned)std::min<size_t>((size_t)s->sm_count * bps, grid);
+        if (pooled)
+            k_closest_persistent<true><<<pgrid, kTraceBlock, 0, stream>>>(s->view, d_rays6, (unsigned int)n, d_id, d_t, s->d_counter);
+        else
+            k_closest_persistent<false><<<pgrid, kTraceBlock, 0, stream>>>(s->view, d_rays6, (unsigned int)n, d_id, d_t, s->d_counter);
     }
     TRT_CUDA(cudaGetLastError());
     s->stats.kernel_launches++;

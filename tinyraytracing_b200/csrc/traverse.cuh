@@ -38,15 +38,14 @@ __device__ __forceinline__ bool boxPass(float3 S, float3 inv, float ax, float ay
     return (t1 >= t0) && (((t0 > 0.0f) ? t0 : t1) > 0.0f);
 }
 
-// interactTriangle (bvh.cpp:177-209) with one extra early-out: a candidate farther than the current best can
-// never be accepted, so its inside test is skipped.
-__device__ __forceinline__ bool triangleHit(const TriGeom &g, float3 S, float3 d, float best_t, float &t_out)
+// plane part: dn = dot(N,d), t = dot(p1-S,N)/dn with the rejections of bvh.cpp:185,189 and the "cannot win" cut
+__device__ __forceinline__ bool trianglePlane(float4 q0, float4 q1, float3 S, float3 d, float best_t, float &t_out)
 {
-    const float3 N = f3(g.p1nx.w, g.p2ny.w, g.p3nz.w);
+    const float3 N = f3(q0.x, q0.y, q0.z);
     const float dn = dot3(N, d);
     if (fabsf(dn) < 0.00001f)
         return false;
-    const float3 p1 = f3(g.p1nx.x, g.p1nx.y, g.p1nx.z);
+    const float3 p1 = f3(q0.w, q1.x, q1.y);
     const float a = dot3(p1 - S, N);
     // opposite signs (or a == +-0 against a negative dn, ...) give t <= -0 < 0.0005: rejected by bvh.cpp:189
     // whatever the quotient is, so the IEEE division is skipped (a NaN operand is a miss on either path)
@@ -57,13 +56,31 @@ __device__ __forceinline__ bool triangleHit(const TriGeom &g, float3 S, float3 d
         return false;
     if (t > best_t)
         return false;
-    const float3 p2 = f3(g.p2ny.x, g.p2ny.y, g.p2ny.z), p3 = f3(g.p3nz.x, g.p3nz.y, g.p3nz.z);
+    t_out = t;
+    return true;
+}
+
+// inside part (bvh.cpp:191-200): three edge cross products against N, all > 0 or all < 0
+__device__ __forceinline__ bool triangleInside(float4 q0, float4 q1, float4 q2, float3 S, float3 d, float t)
+{
+    const float3 N = f3(q0.x, q0.y, q0.z);
+    const float3 p1 = f3(q0.w, q1.x, q1.y), p2 = f3(q1.z, q1.w, q2.x), p3 = f3(q2.y, q2.z, q2.w);
     const float3 P = S + d * t;
     const float dir1 = dot3(cross3(p2 - p1, P - p1), N);
     const float dir2 = dot3(cross3(p3 - p2, P - p2), N);
     const float dir3 = dot3(cross3(p1 - p3, P - p3), N);
-    t_out = t;
     return (dir1 > 0.f && dir2 > 0.f && dir3 > 0.f) || (dir1 < 0.f && dir2 < 0.f && dir3 < 0.f);
+}
+
+// interactTriangle (bvh.cpp:177-209) with one extra early-out: a candidate farther than the current best can
+// never be accepted, so its inside test is skipped.
+__device__ __forceinline__ bool triangleHit(const TriGeom &g, float3 S, float3 d, float best_t, float &t_out)
+{
+    float t;
+    if (!trianglePlane(g.q0, g.q1, S, d, best_t, t))
+        return false;
+    t_out = t;
+    return triangleInside(g.q0, g.q1, g.q2, S, d, t);
 }
 
 // interactBVHNode (bvh.cpp:211-229) over one reference leaf, merged into the running best by (t, key).
@@ -73,7 +90,7 @@ __device__ __forceinline__ void scanLeaf(const SceneView &sv, int first, int num
     {
         const float4 *gp = reinterpret_cast<const float4 *>(sv.tri_geom + i);
         TriGeom g;
-        g.p1nx = __ldg(gp), g.p2ny = __ldg(gp + 1), g.p3nz = __ldg(gp + 2);
+        g.q0 = __ldg(gp), g.q1 = __ldg(gp + 1), g.q2 = __ldg(gp + 2);
         float t;
         if (triangleHit(g, S, d, hit.t, t))
         {
@@ -343,14 +360,52 @@ __device__ __forceinline__ void walkNodeStep(const SceneView &sv, WalkState &st,
     st.cur = l0;
 }
 
+#define TRT_WALK_WARPS 4 // warps per CTA of every kernel that calls walkPersistent (128 threads)
+
+// Inside tests of n (<= 32) pooled candidates, one per lane; the ray comes from the owner lane's registers.
+__device__ __forceinline__ void walkPoolInside(const SceneView &sv, const WalkState &st, const int32_t *pool_tri,
+                                               const float *pool_t, const int32_t *pool_owner, int n,
+                                               unsigned long long *best, int lane)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const bool valid = lane < n;
+    const int tri = valid ? pool_tri[lane] : 0;
+    const float t = valid ? pool_t[lane] : 0.f;
+    const int owner = valid ? pool_owner[lane] : lane;
+    const float3 S = f3(__shfl_sync(FULL, st.S.x, owner), __shfl_sync(FULL, st.S.y, owner), __shfl_sync(FULL, st.S.z, owner));
+    const float3 d = f3(__shfl_sync(FULL, st.d.x, owner), __shfl_sync(FULL, st.d.y, owner), __shfl_sync(FULL, st.d.z, owner));
+    if (valid)
+    {
+        const float4 *gp = reinterpret_cast<const float4 *>(sv.tri_geom + tri);
+        if (triangleInside(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), S, d, t))
+            atomicMin(best + owner, ((unsigned long long)__float_as_uint(t) << 32) | __ldg(sv.tri_rank + tri));
+    }
+}
+
 // RAYS: struct with  __device__ bool load(size_t i, float3 &S, float3 &d)  and  void store(size_t i, const Hit &).
 // `counter` must be zero at launch; n = number of rays.  Every thread of the block must call this.
-template <typename RAYS>
+// POOLED selects the leaf phase: false = every lane scans its own leaf (scanLeaf); true = the warp pools the
+// candidates that pass the plane test and deals their inside tests out one per lane (see below; measured in
+// profiles/r01_closest_staircase_pooled.txt: 8 % fewer instructions at 15 instead of 9.5 lanes, but the shorter
+// dependent chains expose L1 latency — 69 % instead of 83 % issue-active — and it is 9 % slower, so it is off
+// by default and kept selectable (TRT_TRACE_POOLED) for the next round's latency work).
+template <bool POOLED, typename RAYS>
 __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, unsigned int n, unsigned int *counter)
 {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int kRefillIdle = 8; // refill once this many lanes of the warp are idle
     const int lane = threadIdx.x & 31;
+    // per warp: pool of (triangle, t, owner lane) candidates awaiting their inside test, and each lane's best
+    // (t bits << 32 | rank) so far
+    constexpr int kPoolWarps = POOLED ? TRT_WALK_WARPS : 1, kPoolSlots = POOLED ? 64 : 1, kBestSlots = POOLED ? 32 : 1;
+    __shared__ int32_t s_pool_tri[kPoolWarps][kPoolSlots];
+    __shared__ float s_pool_t[kPoolWarps][kPoolSlots];
+    __shared__ int32_t s_pool_owner[kPoolWarps][kPoolSlots];
+    __shared__ unsigned long long s_best[kPoolWarps][kBestSlots];
+    const int warp = POOLED ? (threadIdx.x >> 5) : 0;
+    int32_t *pool_tri = s_pool_tri[warp], *pool_owner = s_pool_owner[warp];
+    float *pool_t = s_pool_t[warp];
+    unsigned long long *best = s_best[warp];
     int32_t stack_link[TRT_WIDE_STACK];
     float stack_t[TRT_WIDE_STACK];
     WalkState st;
@@ -389,6 +444,8 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                     }
                     else
                     {
+                        if (POOLED)
+                            best[lane] = ((unsigned long long)__float_as_uint(TRT_INF) << 32) | sv.miss_rank;
                         st.inv = rcpDir(st.d);
                         stack_link[0] = TRT_LINK_EXIT, stack_t[0] = -1.f;
                         st.sp = 1;
@@ -419,13 +476,68 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                 }
             }
         }
-        // ---- leaves
+        // ---- leaves: every lane runs the plane part for the triangles of ITS leaf; the candidates of the whole warp
+        // are pooled in shared memory and their inside tests (two thirds of a triangle test) are dealt out 32 at a
+        // time, one per lane, whoever owns the ray — ncu on the per-lane scan: 65 % of issued instructions were
+        // triangle tests at 7-10 of 32 lanes.  Results merge through a 64-bit atomicMin on (t bits, rank).
         while (__any_sync(FULL, live && st.leaf != TRT_LINK_EMPTY))
         {
-            if (live && st.leaf != TRT_LINK_EMPTY)
+            const bool has = live && st.leaf != TRT_LINK_EMPTY;
+            if (!POOLED)
             {
-                const int leaf = ~st.leaf;
-                scanLeaf(sv, leaf >> 3, (leaf & 7) + 1, st.S, st.d, st.hit);
+                if (has)
+                {
+                    const int lf = ~st.leaf;
+                    scanLeaf(sv, lf >> 3, (lf & 7) + 1, st.S, st.d, st.hit);
+                    if (st.cur < 0 && st.cur != TRT_LINK_EXIT)
+                    {
+                        st.leaf = st.cur; // a second leaf was reached while the first was postponed
+                        TRT_WALK_POP(st, stack_link, stack_t);
+                    }
+                    else
+                        st.leaf = TRT_LINK_EMPTY;
+                }
+                continue;
+            }
+            const int leaf = has ? ~st.leaf : 0;
+            const int first = leaf >> 3, num = has ? (leaf & 7) + 1 : 0;
+            const int maxnum = __reduce_max_sync(FULL, num);
+            int cnt = 0; // candidates waiting in the pool (warp-uniform)
+            for (int k = 0; k < maxnum; ++k)
+            {
+                bool cand = false;
+                float t = 0.f;
+                if (k < num)
+                {
+                    const float4 *gp = reinterpret_cast<const float4 *>(sv.tri_geom + first + k);
+                    cand = trianglePlane(__ldg(gp), __ldg(gp + 1), st.S, st.d, st.hit.t, t);
+                }
+                const unsigned m = __ballot_sync(FULL, cand);
+                if (m == 0)
+                    continue;
+                if (cand)
+                {
+                    const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+                    pool_tri[pos] = first + k, pool_t[pos] = t, pool_owner[pos] = lane;
+                }
+                cnt += __popc(m);
+                if (cnt >= 32)
+                {
+                    __syncwarp();
+                    walkPoolInside(sv, st, pool_tri + (cnt - 32), pool_t + (cnt - 32), pool_owner + (cnt - 32), 32, best, lane);
+                    cnt -= 32;
+                    __syncwarp();
+                }
+            }
+            if (cnt > 0)
+            {
+                __syncwarp();
+                walkPoolInside(sv, st, pool_tri, pool_t, pool_owner, cnt, best, lane);
+            }
+            __syncwarp();
+            st.hit.t = __uint_as_float((unsigned int)(best[lane] >> 32)); // tighter pruning bound for what follows
+            if (has)
+            {
                 if (st.cur < 0 && st.cur != TRT_LINK_EXIT)
                 {
                     st.leaf = st.cur; // a second leaf was reached while the first was postponed
@@ -438,6 +550,12 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
         // ---- finished rays
         if (live && st.cur == TRT_LINK_EXIT && st.leaf == TRT_LINK_EMPTY)
         {
+            if (POOLED)
+            {
+                const unsigned long long b = best[lane];
+                st.hit.t = __uint_as_float((unsigned int)(b >> 32));
+                st.hit.id = __ldg(sv.rank_tri + (unsigned int)b);
+            }
             rays.store(ray, st.hit);
             ray = 0xffffffffu;
         }

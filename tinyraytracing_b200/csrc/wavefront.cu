@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kBlock) k_trace(SceneView sv, WfBuffers wf, in
     if (MODE != 0)
         traceGridStride<MODE>(sv, r, n);
     else
-        walkPersistent(sv, r, n, reinterpret_cast<unsigned int *>(wf.counters + kPoolTrace));
+        walkPersistent<false>(sv, r, n, reinterpret_cast<unsigned int *>(wf.counters + kPoolTrace));
 }
 
 template <int MODE>
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(kBlock) k_shadow(SceneView sv, WfBuffers wf)
     if (MODE != 0)
         traceGridStride<MODE>(sv, r, n);
     else
-        walkPersistent(sv, r, n, reinterpret_cast<unsigned int *>(wf.counters + kPoolShadow));
+        walkPersistent<false>(sv, r, n, reinterpret_cast<unsigned int *>(wf.counters + kPoolShadow));
 }
 
 // ------------------------------------------------------------------------------------------------ K3

@@ -81,12 +81,16 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Samples before this point (warm-up) are dropped; if none arrives after it, the last one before is kept."""
+        self.mark_at = len(self.lines)
 
     def stop(self):
         if not self.proc:
@@ -100,7 +104,9 @@ class ClockSampler:
         self.t.join(timeout=2)
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        start = getattr(self, "mark_at", 0)
+        lines = self.lines[start:] if len(self.lines) > start else self.lines[-1:]
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -147,7 +153,7 @@ def run_reference(args):
     import refbridge
 
     if not refbridge.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref.so not built (run __graft_entry__.build() in the build container)"}))
+        emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref.so not built (run __graft_entry__.build() in the build container)"}))
         return 0
     with tempfile.TemporaryDirectory() as tmp:
         f = materialize_scene(tmp)
@@ -174,7 +180,7 @@ def run_reference(args):
         dt = time.perf_counter() - t0
         mrays = n * args.steps / dt / 1e6
         sample = "%d rays of the %d-ray batch per step" % (n, N_RAYS)
-        print(json.dumps({
+        emit(json.dumps({
             "impl": "reference", "metric": "Mrays/s (closest-hit)", "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -239,12 +245,13 @@ def run_gpu(args):
             torch.cuda.synchronize()
 
         def timed(fn, events):
+            clocks = ClockSampler(local)
+            clocks.start()  # nvidia-smi needs a moment before its first sample: start it ahead of the warm-up
             for _ in range(args.warmup):
                 fn()
             barrier()
             dev.reset_stats()
-            clocks = ClockSampler(local)
-            clocks.start()
+            clocks.mark()
             if events:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
@@ -312,7 +319,7 @@ def run_gpu(args):
             lib.trt_host_free(p)
         dev.close()
     if rank == 0:
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -399,7 +406,34 @@ def render_measurements(args, tmp, rank, world, local, barrier):
                     "sharding": "samples [r*spp/N, (r+1)*spp/N) per rank, scene replicated, one NCCL reduce(sum, f64, W*H*3)"}
         dev.close()
         barrier()
+        if rank == 0 and world == 1 and not args.no_cpu and key == "config3_veach_mis":
+            out[key]["cpu_reference"] = cpu_reference_render(name, w, h, tmp)
     return out
+
+
+def cpu_reference_render(name, w, h, tmp):
+    """The UNMODIFIED reference program (oracle/_ref/ref_cpu, stdin protocol of main.cpp:46-55) on the host cores,
+    on a bounded sample of the config: reduced resolution (same aspect) and spp = host cores so that its
+    `omp parallel for` over samples (main.cpp:79-81) has work for every core; wall clock around the process
+    (load + BVH build included, small for this scene); scaled linearly in pixel-samples."""
+    from tinyraytracing_b200 import scenes
+
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_cpu")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/ref_cpu not built"}
+    cores = os.cpu_count() or 1
+    sw, sh, spp = w // 5, h // 5, max(8, min(cores, 50))
+    d = os.path.join(tmp, "cpu_ref_" + name)
+    f = scenes.materialize(name, d, width=sw, height=sh)
+    inp = "%s\n%s\n%s\n%s\n%d\n" % (f["basedir"], f["mtl"], f["xml"], f["obj"], spp)
+    t0 = time.perf_counter()
+    r = subprocess.run([exe], input=inp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, text=True, timeout=600)
+    dt = time.perf_counter() - t0
+    if r.returncode != 0:
+        return {"unavailable": "ref_cpu exited %d" % r.returncode}
+    pxs = sw * sh * spp / dt
+    return {"kind": "reference", "cores": cores, "sample": "%dx%d, %d spp, %.1f s wall" % (sw, sh, spp, dt),
+            "pixel_samples_per_s": pxs, "spp_per_s_at_config": pxs / (w * h)}
 
 
 def extra_measurements(args, tmp):
@@ -456,7 +490,25 @@ def extra_measurements(args, tmp):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything except the ONE JSON line goes to stderr: libraries (NCCL's version banner, the loaders' chatter
+    kept from the reference) write to fd 1 from C code."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -11,13 +11,14 @@ from tinyraytracing_b200 import scenes  # noqa: E402
 
 name, w, h, spp = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 flags = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+batch = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 with tempfile.TemporaryDirectory() as tmp:
     f = scenes.materialize(name, tmp, width=w, height=h)
     host = trt.HostScene.load(f["xml"], f["obj"], f["mtl"], f["basedir"])
     dev = trt.DeviceScene(host, 0)
-    dev.render(1, seed=1, flags=flags)
+    dev.render(spp if batch else 1, seed=1, flags=flags, batch_paths=batch)
     dev.reset_stats()
-    img = dev.render(spp, seed=1, flags=flags)
+    img = dev.render(spp, seed=1, flags=flags, batch_paths=batch)
     st = dev.stats()
     rays = st["rays_closest"] + st["rays_shadow"]
     print("%s %dx%d %d spp: %.2f ms, %.2f spp/s, %.1f Mrays/s (%d closest + %d shadow), %d launches, mean %.4f" % (

@@ -1,0 +1,51 @@
+"""The drop-in driver (tinyraytracing_b200/bin/trt_main: the reference's stdin protocol, main.cpp:46-55, with the
+sample loop replaced by the GPU path) and the resolve / 8-bit pack of imshow (main.cpp:30-38)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import tinyraytracing_b200 as trt
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def gamma_pack(img):
+    # (unsigned char)clamp(pow(v, 1.0f / 2.2f) * 255, 0.0, 255.0)
+    g = np.power(img, np.float64(np.float32(1.0) / np.float32(2.2))) * 255
+    return np.minimum(np.maximum(g, 0.0), 255.0).astype(np.uint8)
+
+
+def test_resolve_pack_matches_imshow(device_scenes):
+    import torch
+
+    dev = device_scenes["back"]
+    acc = torch.zeros(dev.height * dev.width * 3, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    dev.render_accumulate(dev.params(4, seed=3), acc.data_ptr())
+    img, rgb = dev.resolve(acc.data_ptr(), 4, want_rgb8=True)
+    assert np.array_equal(img, dev.render(4, seed=3))
+    ref = gamma_pack(img)
+    # device pow vs libm pow may differ in the last ulp: at most one 8-bit step, on a vanishing fraction of pixels
+    diff = np.abs(rgb.astype(np.int32) - ref.astype(np.int32))
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-3
+
+
+def test_trt_main_renders_the_scene_files(scene_files, device_scenes, tmp_path):
+    import cv2
+
+    exe = os.path.join(ROOT, "tinyraytracing_b200", "bin", "trt_main")
+    assert os.path.exists(exe), "bin/trt_main not built"
+    f = scene_files["back"]
+    spp = 4
+    inp = "%s\n%s\n%s\n%s\n%d\n" % (f["basedir"], f["mtl"], f["xml"], f["obj"], spp)
+    env = dict(os.environ, TRT_SEED="17")
+    r = subprocess.run([exe], input=inp, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Build BVH down." in r.stdout and "Iamge output to" in r.stdout  # the reference's own progress lines
+    png = cv2.imread(os.path.join(f["basedir"], "image%d.png" % spp), cv2.IMREAD_COLOR)[:, :, ::-1]
+    img = device_scenes["back"].render(spp, seed=17)
+    assert png.shape == img.shape
+    assert np.array_equal(png, gamma_pack(img))

@@ -29,18 +29,21 @@ __device__ inline void baryLeastSquares(const float *v9, float3 P, float &bx, fl
             if (s > bn)
                 bn = s, best = j;
         }
-        if (best != k)
+        // column swap k <-> best with compile-time indices only (keeps A and perm in registers)
+#pragma unroll
+        for (int j = k + 1; j < 3; ++j)
         {
+            const bool sw = (best == j);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
             {
-                double tmp = A[i][k];
-                A[i][k] = A[i][best];
-                A[i][best] = tmp;
+                const double a = A[i][k], b = A[i][j];
+                A[i][k] = sw ? b : a;
+                A[i][j] = sw ? a : b;
             }
-            int tp = perm[k];
-            perm[k] = perm[best];
-            perm[best] = tp;
+            const int pa = perm[k], pb = perm[j];
+            perm[k] = sw ? pb : pa;
+            perm[j] = sw ? pa : pb;
         }
         const double norm = sqrt(bn);
         if (norm == 0.0)

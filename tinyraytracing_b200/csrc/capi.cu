@@ -42,7 +42,7 @@ bool isSm100(int device)
 }
 
 // staging for the blocking host-pointer entry point
-constexpr size_t kChunkRays = 1u << 21;
+constexpr size_t kChunkRays = 1u << 19; // small chunks keep the un-overlapped head (first H2D) and tail (last kernel + D2H) short
 
 int ensureStaging(trt_scene *s)
 {

@@ -368,7 +368,10 @@ __global__ void __launch_bounds__(kBlock) k_shade(SceneView sv, WfBuffers wf, in
                     const float3 intensity = (((lm.radiance * cos_theta_p) * cos_theta) / len2) / pdf_light;
                     const float3 h = normalize3((wi + wo) * 0.5f);
                     const double cos_alpha = fmax((double)dot3(pn, h), 0.0);
-                    const float spec = (float)pow(cos_alpha, (double)m.Ns);
+                    // Ks == 0 (every diffuse material): Ks * (Ns+2) * pow(...) is +0 for any finite power, and the
+                    // power is finite for cos_alpha in [0,1] and Ns >= 0 — the double-precision pow is skipped
+                    const bool no_spec = (m.Ks.x == 0.f) && (m.Ks.y == 0.f) && (m.Ks.z == 0.f) && (m.Ns >= 0.f);
+                    const float spec = no_spec ? 0.f : (float)pow(cos_alpha, (double)m.Ns);
                     const float3 brdf = (Kd / kPI) + (((m.Ks * (m.Ns + 2.0f)) * spec) / (2.0f * kPI));
                     const float3 contrib = intensity * brdf;
                     const int cidx = slot * sv.n_lights + li;

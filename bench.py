@@ -381,7 +381,7 @@ def render_measurements(args, tmp, rank, world, local, barrier):
         finally:
             os.dup2(saved, 1)
         dev = trt.DeviceScene(host, local)
-        render_on_gpus(dev, max(world, 2), seed=1)  # warm-up: allocates the wavefront buffers, primes NCCL
+        render_on_gpus(dev, spp, seed=2)  # warm-up at full size: allocates the wavefront buffers, primes NCCL
         barrier()
         dev.reset_stats()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

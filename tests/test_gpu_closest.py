@@ -166,3 +166,63 @@ def test_synthetic_mesh_from_arrays():
     ref, _ = orc.render(4, seed=2)
     assert np.sqrt(((img - ref) ** 2).mean()) <= 1e-3 * ref.mean()
     dev.close()
+
+
+@pytest.mark.parametrize("n_tris", (0, 1, 8, 9))
+def test_degenerate_topologies(n_tris):
+    """Empty scene (NULL root, bvh.cpp:148), a root that is itself a leaf (scanned WITHOUT a box test,
+    bvh.cpp:151-154), and the smallest tree with an inner node; no lights."""
+    import oraclelib
+
+    rng = np.random.default_rng(n_tris)
+    v = rng.uniform(-1, 1, (n_tris, 9)).astype(np.float32)
+    mtl = np.zeros(n_tris, np.int32)
+    mats = [dict(Kd=(0.5, 0.5, 0.5), Ks=(0, 0, 0), Tr=(1, 1, 1), Ns=1.0, Ni=1.0)]
+    cam = dict(eye=(0.0, 0.0, -4.0), lookat=(0.0, 0.0, 0.0), up=(0.0, 1.0, 0.0), fovy=40.0)
+    host = trt.HostScene.from_arrays(v, mtl, mats, [], cam["eye"], cam["lookat"], cam["up"], cam["fovy"], 16, 16)
+    dev = trt.DeviceScene(host, 0)
+    n = 20000
+    o = rng.uniform(-2, 2, (n, 3))
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d], 1).astype(np.float32)
+    if n_tris:
+        # aim half of the rays at triangle interiors so that hits are plentiful
+        tri = v[rng.integers(0, n_tris, n // 2)].reshape(-1, 3, 3)
+        b = rng.dirichlet((1, 1, 1), n // 2)[:, :, None]
+        tgt = (tri * b).sum(1)
+        dd = tgt - rays[: n // 2, :3]
+        rays[: n // 2, 3:] = dd / np.linalg.norm(dd, axis=1, keepdims=True)
+        ps = dict(v=v, vn=np.zeros((n_tris, 9), np.float32), vt=np.zeros((n_tris, 6), np.float32), mtl=mtl,
+                  materials=[dict(mats[0], name="m")], lights=[], textures=[], eye=np.array(cam["eye"], np.float32),
+                  lookat=np.array(cam["lookat"], np.float32), up=np.array(cam["up"], np.float32), fovy=np.float32(40.0),
+                  width=16, height=16)
+        orc = oraclelib.OracleScene(ps)
+        oid, ot = orc.trace(rays)
+        assert (oid >= 0).sum() > n // 8
+    else:
+        oid, ot = np.full(n, -1, np.int32), np.full(n, trt.INF, np.float32)
+    for flags in MODES.values():
+        ids, t = dev.trace_closest(rays, flags)
+        assert np.array_equal(ids, oid) and np.array_equal(t.view(np.uint32), ot.view(np.uint32))
+    img = dev.render(2, seed=1)  # no lights: everything is black, nothing hangs
+    assert img.shape == (16, 16, 3) and np.all(img == 0)
+    dev.close()
+
+
+def test_scene_without_wide_layout(host_scenes, oracle_scenes, monkeypatch):
+    """Scenes whose fast layout would be deeper than its stack keep the reference-topology kernels (every mode,
+    the persistent kernel included, must then walk the reference tree).  Forced here with TRT_WIDE_SOURCE=off."""
+    monkeypatch.setenv("TRT_WIDE_SOURCE", "off")
+    dev = trt.DeviceScene(host_scenes["veach-mis"], 0)
+    monkeypatch.delenv("TRT_WIDE_SOURCE")
+    assert dev.stats()["accel_nodes"] == 390  # inner nodes of the reference tree (781 nodes, 391 leaves)
+    rays = make_rays(host_scenes["veach-mis"], oracle_scenes["veach-mis"], 1 << 18, seed=21)
+    oid, ot = oracle_scenes["veach-mis"].trace(rays)
+    for flags in MODES.values():
+        ids, t = dev.trace_closest(rays, flags)
+        assert np.array_equal(ids, oid) and np.array_equal(t.view(np.uint32), ot.view(np.uint32))
+    ref, _ = oracle_scenes["veach-mis"].render(2, seed=8)
+    img = dev.render(2, seed=8)
+    assert np.sqrt(((img - ref) ** 2).mean()) <= 1e-3 * ref.mean()
+    dev.close()

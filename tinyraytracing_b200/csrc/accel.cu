@@ -287,7 +287,11 @@ std::string buildWide(const trt_scene_desc &desc, AccelBuild &out)
         return "";
     }
     WideBuilder wb{prims, {}, {}};
-    const char *mode = getenv("TRT_WIDE_SOURCE"); // "ref": collapse the reference binary tree as it is (experiments)
+    // TRT_WIDE_SOURCE: "ref" collapses the reference binary tree as it is (experiments); "off" builds no wide
+    // layout at all, which is what happens to scenes too deep for its stack (lets tests cover that path)
+    const char *mode = getenv("TRT_WIDE_SOURCE");
+    if (mode && std::string(mode) == "off")
+        return "wide layout disabled by TRT_WIDE_SOURCE=off";
     if (mode && std::string(mode) == "ref")
     {
         // binary nodes = the reference's, pre-order; leaf prims in the same left-to-right order as `prims`

@@ -457,6 +457,8 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                         st.leaf = TRT_LINK_EMPTY;
                         if (st.cur == TRT_LINK_EMPTY) // empty scene
                             st.cur = TRT_LINK_EXIT;
+                        else if (st.cur < 0) // the whole scene is one reference leaf: scanned without a box test
+                            st.leaf = st.cur, st.cur = TRT_LINK_EXIT;
                     }
                 }
             }

@@ -76,6 +76,31 @@ bool isPinnedOrManaged(const void *p)
 } // namespace
 } // namespace trt
 
+trt_scene::~trt_scene()
+{
+    if (device >= 0)
+        cudaSetDevice(device);
+    cudaDeviceSynchronize();
+    trt::destroyWavefront(this);
+    for (void *p : allocations)
+        cudaFree(p);
+    cudaFree(d_counter);
+    for (int b = 0; b < 2; ++b)
+    {
+        if (stage_in[b])
+            cudaFreeHost(stage_in[b]);
+        if (stage_out[b])
+            cudaFreeHost(stage_out[b]);
+        cudaFree(d_rays[b]), cudaFree(d_id[b]), cudaFree(d_t[b]);
+        for (cudaEvent_t e : {ev_in[b], ev_k[b], ev_out[b], ev[b]})
+            if (e)
+                cudaEventDestroy(e);
+    }
+    for (cudaStream_t st : {stream, copy_in, copy_out})
+        if (st)
+            cudaStreamDestroy(st);
+}
+
 using namespace trt;
 
 extern "C"
@@ -259,29 +284,7 @@ int trt_scene_create(const trt_scene_desc *desc, int device, trt_scene **out)
 
 void trt_scene_destroy(trt_scene *s)
 {
-    if (!s)
-        return;
-    cudaSetDevice(s->device);
-    cudaDeviceSynchronize();
-    destroyWavefront(s);
-    for (void *p : s->allocations)
-        cudaFree(p);
-    cudaFree(s->d_counter);
-    for (int b = 0; b < 2; ++b)
-    {
-        if (s->stage_in[b])
-            cudaFreeHost(s->stage_in[b]);
-        if (s->stage_out[b])
-            cudaFreeHost(s->stage_out[b]);
-        cudaFree(s->d_rays[b]), cudaFree(s->d_id[b]), cudaFree(s->d_t[b]);
-        if (s->ev_in[b])
-            cudaEventDestroy(s->ev_in[b]), cudaEventDestroy(s->ev_k[b]), cudaEventDestroy(s->ev_out[b]);
-    }
-    if (s->ev[0])
-        cudaEventDestroy(s->ev[0]), cudaEventDestroy(s->ev[1]);
-    if (s->stream)
-        cudaStreamDestroy(s->stream), cudaStreamDestroy(s->copy_in), cudaStreamDestroy(s->copy_out);
-    delete s;
+    delete s; // ~trt_scene releases every device / pinned allocation, stream and event
 }
 
 int trt_trace_closest_async(trt_scene *s, const float *d_rays6, size_t n, int32_t *d_id, float *d_t, uint32_t flags,
@@ -433,11 +436,14 @@ int trt_trace_counters(trt_scene *s, const float *rays6, size_t n, uint64_t out4
         cudaFree(d_r);
         return fail(TRT_ERR_CUDA, "cudaMalloc failed");
     }
-    cudaMemcpyAsync(d_r, rays6, n * 24, cudaMemcpyHostToDevice, s->stream);
-    cudaMemsetAsync(d_o, 0, 32, s->stream);
-    int rc = launchClosestCounters(s, d_r, n, d_o, s->stream);
-    cudaMemcpyAsync(out4, d_o, 32, cudaMemcpyDeviceToHost, s->stream);
-    cudaError_t e = cudaStreamSynchronize(s->stream);
+    cudaError_t e = cudaMemcpyAsync(d_r, rays6, n * 24, cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess)
+        e = cudaMemsetAsync(d_o, 0, 32, s->stream);
+    int rc = (e == cudaSuccess) ? launchClosestCounters(s, d_r, n, d_o, s->stream) : TRT_OK;
+    if (e == cudaSuccess && rc == TRT_OK)
+        e = cudaMemcpyAsync(out4, d_o, 32, cudaMemcpyDeviceToHost, s->stream);
+    const cudaError_t es = cudaStreamSynchronize(s->stream);
+    e = (e == cudaSuccess) ? es : e;
     cudaFree(d_r), cudaFree(d_o);
     if (rc == TRT_OK && e != cudaSuccess)
         return fail(TRT_ERR_CUDA, std::string("trt_trace_counters: ") + cudaGetErrorString(e));

@@ -25,7 +25,11 @@ struct Wavefront; // wavefront.cu
 
 struct trt_scene
 {
-    int device = 0;
+    trt_scene() = default;
+    trt_scene(const trt_scene &) = delete;
+    trt_scene &operator=(const trt_scene &) = delete;
+    ~trt_scene(); // capi.cu: frees everything below, so every early return of trt_scene_create cleans up
+    int device = -1;
     int sm_count = 148;
     trt::SceneView view{};
     std::vector<void *> allocations; // every cudaMalloc owned by the scene

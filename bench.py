@@ -311,6 +311,8 @@ def run_gpu(args):
                                "note": "scene is L1/L2 resident (2 kB): the HBM-denominated figure is for cross-config comparison, SURVEY §8d"}
         if not args.no_render:
             out["render"] = render_measurements(args, tmp, rank, world, local, barrier)
+            if rank == 0 and world == 1:
+                out["cornell_standin"] = standin_measurements(args)
         if rank == 0 and world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(f, rays)
         if args.extra and rank == 0 and world == 1:
@@ -408,6 +410,53 @@ def render_measurements(args, tmp, rank, world, local, barrier):
         barrier()
         if rank == 0 and world == 1 and not args.no_cpu and key == "config3_veach_mis":
             out[key]["cpu_reference"] = cpu_reference_render(name, w, h, tmp)
+    return out
+
+
+def standin_measurements(args):
+    """Configs 1/2 on the labelled STAND-IN for the missing cornell-box.obj (Cornell shell + 100k-triangle displaced
+    sphere, tinyraytracing_b200.scenes.cornell_with_standin): closest-hit Mrays/s of a 4 Mi config-2 batch and the
+    512x512 16-spp render of config 1, reference behaviour (RR only) and with the added max-depth-5 truncation."""
+    import torch
+
+    import tinyraytracing_b200 as trt
+    from tinyraytracing_b200 import scenes, workloads
+
+    a = scenes.cornell_with_standin()
+    host = trt.HostScene.from_arrays(a["v9"], a["mtl"], a["materials"], a["lights"], a["eye"], a["lookat"], a["up"], a["fovy"],
+                                     a["width"], a["height"], vn9=a["vn9"], vt6=a["vt6"])
+    dev = trt.DeviceScene(host, 0)
+
+    def tracer(rays):
+        ids, t = dev.trace_closest(rays)
+        hp, pn = dev.hit_attributes(rays, ids, t)
+        return ids, hp, pn
+
+    n = 4 << 20
+    rays = workloads.fixed_ray_batch(n, host.camera(), host.root_box(), tracer)
+    d_rays = torch.from_numpy(rays).cuda()
+    d_id = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_t = torch.empty(n, dtype=torch.float32, device="cuda")
+    sp = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        dev.trace_closest_async(d_rays.data_ptr(), n, d_id.data_ptr(), d_t.data_ptr(), args.flags, sp)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        dev.trace_closest_async(d_rays.data_ptr(), n, d_id.data_ptr(), d_t.data_ptr(), args.flags, sp)
+    e1.record()
+    torch.cuda.synchronize()
+    out = {"what": "STAND-IN, not reference geometry: test/back shell + displaced sphere", "tris": int(host.n_tris),
+           "ref_depth": dev.stats()["ref_depth"], "closest_hit_mrays": 5 * n / (e0.elapsed_time(e1) * 1e-3) / 1e6}
+    for key, md in (("render_512x512_16spp", 0), ("render_512x512_16spp_maxdepth5", 5)):
+        dev.render(16, seed=1, max_depth=md)
+        dev.reset_stats()
+        dev.render(16, seed=1, max_depth=md)
+        st = dev.stats()
+        out[key] = {"ms": st["last_render_ms"], "spp_per_s": 16 / (st["last_render_ms"] * 1e-3),
+                    "mrays_per_s": (st["rays_closest"] + st["rays_shadow"]) / (st["last_render_ms"] * 1e-3) / 1e6}
+    dev.close()
+    host.close()
     return out
 
 

@@ -53,62 +53,10 @@ def available():
 
 
 def parsed_scene(name, width=None, height=None):
-    """Parsed (pre-build, OBJ-order) scene arrays straight from scenes/<name>.npz — independent of both the
-    product's C++ loader and the reference's: numbers are converted with numpy float32 (== stof)."""
-    import cv2
+    """Parsed (pre-build, OBJ-order) scene arrays straight from scenes/<name>.npz (tinyraytracing_b200.scenes.parsed)."""
+    from tinyraytracing_b200 import scenes
 
-    z = np.load(os.path.join(ROOT, "scenes", name + ".npz"))
-    meta = json.loads(str(z["meta"]))
-    faces = z["faces"]  # (n, 3 corners, 3 slots v/vt/vn or v/vn/vt)
-    v, vn, vt = z["v"], z["vn"], z["vt"]
-    s2, s3 = (2, 1) if not meta["isvnvt"] else (1, 2)  # column of vn, column of vt
-    tri_v = v[faces[:, :, 0] - 1].reshape(-1, 9)
-    tri_vn = vn[faces[:, :, s2] - 1].reshape(-1, 9)
-    tri_vt = vt[faces[:, :, s3] - 1].reshape(-1, 6)
-    # materials: names in order of first appearance: lights (xml), obj usemtl, mtl newmtl
-    xml = meta["xml"]
-    names = []
-    for l in xml["lights"]:
-        if l["mtlname"] not in names:
-            names.append(l["mtlname"])
-    for nme in meta["obj_mtl_names"]:
-        if nme not in names:
-            names.append(nme)
-    mats = {}
-    cur = ""
-    tex_files = []
-    for tok in meta["mtl"]:
-        k = tok[0]
-        if k == "newmtl":
-            cur = tok[1]
-        elif k in ("Kd", "Ks", "Tr"):
-            mats.setdefault(cur, {})[k] = [np.float32(x) for x in tok[1:4]]
-        elif k in ("Ns", "Ni"):
-            mats.setdefault(cur, {})[k] = np.float32(tok[1])
-        elif k == "map_Kd":
-            mats.setdefault(cur, {})["map_Kd"] = tok[1]
-            if tok[1] not in tex_files:
-                tex_files.append(tok[1])
-    for nme in mats:
-        if nme not in names:
-            names.append(nme)
-    textures = [cv2.imdecode(z["jpeg:" + f], cv2.IMREAD_COLOR) for f in tex_files]
-    materials = []
-    for nme in names:
-        m = mats.get(nme, {})
-        materials.append(dict(name=nme, Kd=m.get("Kd", [0, 0, 0]), Ks=m.get("Ks", [0, 0, 0]), Tr=m.get("Tr", [0, 0, 0]),
-                              Ns=m.get("Ns", 1.0), Ni=m.get("Ni", 1.0),
-                              texture=tex_files.index(m["map_Kd"]) if "map_Kd" in m else -1))
-    face_mtl = np.array([names.index(meta["obj_mtl_names"][i]) for i in z["face_mtl"]], np.int32)
-    lights = []
-    for l in xml["lights"]:
-        rs = l["radiance"].split(",")
-        lights.append((names.index(l["mtlname"]), [np.float32(x) for x in rs[:3]]))
-    f3 = lambda d: np.array([np.float32(d["x"]), np.float32(d["y"]), np.float32(d["z"])], np.float32)
-    cam = xml["camera"]
-    return dict(name=name, v=tri_v, vn=tri_vn, vt=tri_vt, mtl=face_mtl, materials=materials, lights=lights,
-                textures=textures, eye=f3(xml["eye"]), lookat=f3(xml["lookat"]), up=f3(xml["up"]),
-                fovy=np.float32(cam["fovy"]), width=int(width or cam["width"]), height=int(height or cam["height"]))
+    return scenes.parsed(name, width, height)
 
 
 class OracleScene:

@@ -113,3 +113,81 @@ def materialize(name, outdir, width=None, height=None):
 
     return dict(basedir=outdir, obj=os.path.join(outdir, stem + ".obj"), mtl=os.path.join(outdir, stem + ".mtl"),
                 xml=os.path.join(outdir, stem + ".xml"), width=int(cam["width"]), height=int(cam["height"]))
+
+
+def parsed(name, width=None, height=None):
+    """Parsed (pre-build, OBJ-order) scene arrays straight from scenes/<name>.npz — independent of both the
+    product's C++ loader and the reference's: numbers are converted with numpy float32 (== stof)."""
+    import cv2
+
+    z = np.load(os.path.join(SCENE_DIR, name + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    faces = z["faces"]  # (n, 3 corners, 3 slots v/vt/vn or v/vn/vt)
+    v, vn, vt = z["v"], z["vn"], z["vt"]
+    s2, s3 = (2, 1) if not meta["isvnvt"] else (1, 2)  # column of vn, column of vt
+    tri_v = v[faces[:, :, 0] - 1].reshape(-1, 9)
+    tri_vn = vn[faces[:, :, s2] - 1].reshape(-1, 9)
+    tri_vt = vt[faces[:, :, s3] - 1].reshape(-1, 6)
+    # materials: names in order of first appearance: lights (xml), obj usemtl, mtl newmtl
+    xml = meta["xml"]
+    names = []
+    for l in xml["lights"]:
+        if l["mtlname"] not in names:
+            names.append(l["mtlname"])
+    for nme in meta["obj_mtl_names"]:
+        if nme not in names:
+            names.append(nme)
+    mats = {}
+    cur = ""
+    tex_files = []
+    for tok in meta["mtl"]:
+        k = tok[0]
+        if k == "newmtl":
+            cur = tok[1]
+        elif k in ("Kd", "Ks", "Tr"):
+            mats.setdefault(cur, {})[k] = [np.float32(x) for x in tok[1:4]]
+        elif k in ("Ns", "Ni"):
+            mats.setdefault(cur, {})[k] = np.float32(tok[1])
+        elif k == "map_Kd":
+            mats.setdefault(cur, {})["map_Kd"] = tok[1]
+            if tok[1] not in tex_files:
+                tex_files.append(tok[1])
+    for nme in mats:
+        if nme not in names:
+            names.append(nme)
+    textures = [cv2.imdecode(z["jpeg:" + f], cv2.IMREAD_COLOR) for f in tex_files]
+    materials = []
+    for nme in names:
+        m = mats.get(nme, {})
+        materials.append(dict(name=nme, Kd=m.get("Kd", [0, 0, 0]), Ks=m.get("Ks", [0, 0, 0]), Tr=m.get("Tr", [0, 0, 0]),
+                              Ns=m.get("Ns", 1.0), Ni=m.get("Ni", 1.0),
+                              texture=tex_files.index(m["map_Kd"]) if "map_Kd" in m else -1))
+    face_mtl = np.array([names.index(meta["obj_mtl_names"][i]) for i in z["face_mtl"]], np.int32)
+    lights = []
+    for l in xml["lights"]:
+        rs = l["radiance"].split(",")
+        lights.append((names.index(l["mtlname"]), [np.float32(x) for x in rs[:3]]))
+    f3 = lambda d: np.array([np.float32(d["x"]), np.float32(d["y"]), np.float32(d["z"])], np.float32)
+    cam = xml["camera"]
+    return dict(name=name, v=tri_v, vn=tri_vn, vt=tri_vt, mtl=face_mtl, materials=materials, lights=lights,
+                textures=textures, eye=f3(xml["eye"]), lookat=f3(xml["lookat"]), up=f3(xml["up"]),
+                fovy=np.float32(cam["fovy"]), width=int(width or cam["width"]), height=int(height or cam["height"]))
+
+
+def cornell_with_standin(nq=224, width=512, height=512):
+    """BASELINE configs 1/2 name the cornell-box scene, whose mesh (cornell-box.obj, the dragon) is a missing blob in the
+    reference checkout.  STAND-IN, clearly not the reference's geometry: the Cornell shell `test/back` (same camera,
+    materials, light) plus a procedurally displaced sphere of 2*nq^2 triangles (nq = 224 -> 100 352) in material
+    DiffuseWhite standing on the floor.  Returns the arguments of HostScene.from_arrays."""
+    from . import workloads
+
+    ps = parsed("back", width, height)
+    m = workloads.stress_mesh(nq, radius=110.0, center=(278.0, 135.0, 300.0))
+    n_sphere = 2 * nq * nq
+    white = [i for i, mm in enumerate(ps["materials"]) if mm["name"].endswith("DiffuseWhite")][0]
+    v = np.concatenate([ps["v"], m["v9"][:n_sphere]]).astype(np.float32)
+    vn = np.concatenate([ps["vn"], m["vn9"][:n_sphere]]).astype(np.float32)
+    vt = np.concatenate([ps["vt"], np.zeros((n_sphere, 6), np.float32)])
+    mtl = np.concatenate([ps["mtl"], np.full(n_sphere, white, np.int32)]).astype(np.int32)
+    return dict(v9=v, vn9=vn, vt6=vt, mtl=mtl, materials=ps["materials"], lights=ps["lights"], eye=ps["eye"],
+                lookat=ps["lookat"], up=ps["up"], fovy=float(ps["fovy"]), width=width, height=height)

@@ -182,6 +182,8 @@ typedef struct trt_stats {
     int32_t accel_leaves;  /* reference leaves (bvh.cpp:43-48) kept as scan units                       */
     int32_t ref_depth;     /* depth of the reference tree                                               */
     int32_t device;
+    int32_t accel_slivers; /* triangles boxed with the larger sliver pad (fast layout)                    */
+    int32_t accel_needles; /* triangles left under their reference leaf's box (fast layout)               */
 } trt_stats;
 
 int trt_get_stats(trt_scene *scene, trt_stats *out);

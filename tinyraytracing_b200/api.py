@@ -54,7 +54,7 @@ class Stats(C.Structure):
     _fields_ = [("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64), ("paths", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("last_render_ms", C.c_double), ("last_trace_ms", C.c_double),
                 ("accel_nodes", C.c_int32), ("accel_leaves", C.c_int32), ("ref_depth", C.c_int32),
-                ("device", C.c_int32)]
+                ("device", C.c_int32), ("accel_slivers", C.c_int32), ("accel_needles", C.c_int32)]
 
 
 # every symbol include/trt.h and include/trt_host.h declare (tests check the library exports all of them)

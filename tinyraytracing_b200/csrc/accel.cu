@@ -129,10 +129,14 @@ std::string buildAccel(const trt_scene_desc &desc, AccelBuild &out)
 } // namespace trt
 
 // ------------------------------------------------------------------------------------------------------------
-// Fast layout: binned-SAH binary tree over the reference's leaves, collapsed to 4 children per node.
-// The reference tree's upper levels are median-x splits (its SAH is capped at INF = 114514, bvh.cpp:49-51,
-// 125-134), which costs ~140 box tests per ray on staircase; the leaves themselves stay the scan units, so
-// the set of triangles tested together — and with it the reference's result — is unchanged (traverse.cuh).
+// Fast layout: binned-SAH binary tree collapsed to 4 children per node, built over
+//   "triangles" (default)  the scene's triangles, own leaves of <= 4 triangles, boxes padded generously; a hit is
+//                          accepted only if the triangle's REFERENCE leaf box also passes the reference's slab test
+//   "leaves"               the reference's leaves as atomic scan units with their own boxes bit for bit
+// (TRT_WIDE_SOURCE selects; "off" builds nothing).  Why not keep the reference's leaves: its SAH is capped at
+// INF = 114514 (bvh.cpp:49-51,125-134), so in any scene with coordinates beyond a few tens of units EVERY split
+// is a median split on x and the leaves are thin x-slabs spanning the whole object (Cornell shell + 100k-triangle
+// sphere: median leaf extent 192 units, 60 leaves / 367 triangle tests per ray).
 namespace trt
 {
 namespace
@@ -140,13 +144,14 @@ namespace
 struct Prim
 {
     float lo[3], hi[3], c[3];
-    int32_t link;
-    float w; // scan cost of the leaf: one box test + num triangle tests
+    int32_t payload; // triangle index (triangle mode) or reference leaf ordinal (leaf mode)
+    float w;
 };
 struct BNode
 {
     float lo[3], hi[3];
-    int32_t left = -1, right = -1; // binary children, or prim index in `left` when right == -2
+    int32_t left = -1, right = -1; // children; for a leaf: right == -2 and [first, first + count) of `order`
+    int32_t first = 0, count = 0;
 };
 
 inline float halfArea(const float *lo, const float *hi)
@@ -166,6 +171,7 @@ inline void grow(float *lo, float *hi, const float *plo, const float *phi)
 struct WideBuilder
 {
     std::vector<Prim> &prims;
+    int maxLeaf;
     std::vector<int32_t> order;
     std::vector<BNode> bn;
 
@@ -183,10 +189,9 @@ struct WideBuilder
         }
         for (int a = 0; a < 3; ++a)
             bn[me].lo[a] = lo[a], bn[me].hi[a] = hi[a];
-        if (r - l == 1)
+        if (r - l <= maxLeaf)
         {
-            bn[me].left = order[l];
-            bn[me].right = -2;
+            bn[me].right = -2, bn[me].first = l, bn[me].count = r - l;
             return me;
         }
         constexpr int NB = 32;
@@ -264,64 +269,154 @@ std::string buildWide(const trt_scene_desc &desc, AccelBuild &out)
     out.wide_nodes.clear();
     out.wide_root = TRT_LINK_EMPTY;
     out.wide_depth = 0;
-    const int nn = desc.n_nodes;
-    std::vector<Prim> prims;
+    out.fast_geom.clear(), out.fast_key.clear(), out.fast_rank.clear(), out.fast_orig.clear(), out.fast_leaf.clear();
+    out.ref_leaf_box.clear();
+    const int nn = desc.n_nodes, n = desc.n_tris;
+    const char *env = getenv("TRT_WIDE_SOURCE");
+    const std::string mode = env ? env : "triangles";
+    if (mode == "off")
+        return "wide layout disabled by TRT_WIDE_SOURCE=off";
+    const bool leafMode = (mode == "leaves");
+
+    // reference leaves: box, triangle range, and the leaf each triangle belongs to
+    struct RefLeaf
+    {
+        int32_t first, num;
+    };
+    std::vector<RefLeaf> leaves;
+    std::vector<int32_t> leafOfTri(n, -1);
+    float scale = 0.f;
     for (int i = 0; i < nn; ++i)
     {
         const int32_t *lk = desc.node_link + (size_t)i * 4;
         if (lk[3] <= 0)
             continue;
         const float *b = desc.node_box + (size_t)i * 6;
-        Prim p;
-        for (int a = 0; a < 3; ++a)
-            p.lo[a] = b[a], p.hi[a] = b[3 + a], p.c[a] = 0.5f * (b[a] + b[3 + a]);
-        p.link = ~((lk[2] << 3) | (lk[3] - 1));
-        p.w = 1.0f + (float)lk[3];
-        prims.push_back(p);
+        out.ref_leaf_box.push_back(make_float4(b[0], b[1], b[2], 0.f));
+        out.ref_leaf_box.push_back(make_float4(b[3], b[4], b[5], 0.f));
+        for (int k = 0; k < lk[3]; ++k)
+            leafOfTri[lk[2] + k] = (int32_t)leaves.size();
+        leaves.push_back({lk[2], lk[3]});
+        for (int a = 0; a < 6; ++a)
+            if (std::isfinite(b[a]))
+                scale = std::fmax(scale, std::fabs(b[a]));
     }
-    if (prims.empty())
+    if (leaves.empty())
         return "";
-    if (prims.size() == 1)
+    // a reference tree that is ONE leaf is scanned without any box test (bvh.cpp:151-154): no per-hit box check then
+    out.root_is_reference_leaf = (leaves.size() == 1);
+
+    // Own boxes are padded by 256 ulp(scene scale), scale = largest |coordinate| of the reference leaf boxes.  A
+    // reported hit point S + d*t lies within a few ulp(|S| + t) of its (non-sliver) triangle, and rays whose origin
+    // is farther than 4 * scale from the coordinate origin take the strict walk, so the ray passes the padded box of
+    // every triangle it can hit with a margin of well over ten times the rounding of the slab test.
+    // A pad tied to the scale rather than a fixed length matters for finely tessellated geometry: staircase has
+    // 25 920 millimetre-sized triangles, which a fixed 4e-3 pad would blow up eightfold.
+    const float pad = 256.f * (std::nextafter(scale, INFINITY) - scale) + 1e-30f;
+    out.scene_scale = scale;
+    std::vector<Prim> prims;
+    if (leafMode)
     {
-        out.wide_root = prims[0].link; // the reference scans a root leaf without any box test (bvh.cpp:151-154)
-        return "";
-    }
-    WideBuilder wb{prims, {}, {}};
-    // TRT_WIDE_SOURCE: "ref" collapses the reference binary tree as it is (experiments); "off" builds no wide
-    // layout at all, which is what happens to scenes too deep for its stack (lets tests cover that path)
-    const char *mode = getenv("TRT_WIDE_SOURCE");
-    if (mode && std::string(mode) == "off")
-        return "wide layout disabled by TRT_WIDE_SOURCE=off";
-    if (mode && std::string(mode) == "ref")
-    {
-        // binary nodes = the reference's, pre-order; leaf prims in the same left-to-right order as `prims`
-        std::vector<int32_t> leafPrim(nn, -1);
-        int32_t lp = 0;
-        for (int i = 0; i < nn; ++i)
-            if (desc.node_link[(size_t)i * 4 + 3] > 0)
-                leafPrim[i] = lp++;
-        wb.bn.resize(nn);
-        for (int i = 0; i < nn; ++i)
+        for (size_t l = 0; l < leaves.size(); ++l)
         {
-            const int32_t *lk = desc.node_link + (size_t)i * 4;
-            const float *b = desc.node_box + (size_t)i * 6;
+            Prim p;
+            const float4 lo = out.ref_leaf_box[2 * l], hi = out.ref_leaf_box[2 * l + 1];
+            p.lo[0] = lo.x, p.lo[1] = lo.y, p.lo[2] = lo.z, p.hi[0] = hi.x, p.hi[1] = hi.y, p.hi[2] = hi.z;
             for (int a = 0; a < 3; ++a)
-                wb.bn[i].lo[a] = b[a], wb.bn[i].hi[a] = b[3 + a];
-            if (lk[3] > 0)
-                wb.bn[i].left = leafPrim[i], wb.bn[i].right = -2;
-            else
-                wb.bn[i].left = lk[0], wb.bn[i].right = lk[1];
+                p.c[a] = 0.5f * (p.lo[a] + p.hi[a]);
+            p.payload = (int32_t)l;
+            p.w = 1.0f + (float)leaves[l].num;
+            prims.push_back(p);
         }
     }
     else
     {
-        wb.order.resize(prims.size());
-        for (size_t i = 0; i < prims.size(); ++i)
-            wb.order[i] = (int32_t)i;
-        wb.bn.reserve(prims.size() * 2);
-        wb.build(0, (int)prims.size());
+        for (int t = 0; t < n; ++t)
+        {
+            const float *v = desc.v + (size_t)t * 9, *N = desc.normal + (size_t)t * 3;
+            bool ok = leafOfTri[t] >= 0 && std::isfinite(N[0]) && std::isfinite(N[1]) && std::isfinite(N[2]);
+            for (int k = 0; k < 9; ++k)
+                ok = ok && std::isfinite(v[k]);
+            if (!ok)
+                continue; // a NaN normal / non-finite vertex can never pass interactTriangle's comparisons
+            Prim p;
+            // Needle / sliver triangles: the three edge tests of interactTriangle bound the hit point only up to
+            // (rounding noise) / sin(smallest angle): an accepted point may lie beyond the triangle along its long
+            // axis by about ext = 1e-6 * emax / (height / emax)  (1e-6 = twice the ~8-operation float noise of an edge
+            // test relative to |edge| |P - p|).  The triangle's box is padded by max(pad, 4 ext); a needle so thin that
+            // 4 ext exceeds a quarter of its length keeps the box the reference itself culls it with — its reference
+            // leaf's — and so behaves exactly as in the leaf-atomic layout.
+            const double e1[3] = {(double)v[3] - v[0], (double)v[4] - v[1], (double)v[5] - v[2]};
+            const double e2[3] = {(double)v[6] - v[0], (double)v[7] - v[1], (double)v[8] - v[2]};
+            const double e3[3] = {(double)v[6] - v[3], (double)v[7] - v[4], (double)v[8] - v[5]};
+            const double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+            const double area2 = std::sqrt(cx * cx + cy * cy + cz * cz);
+            double emax2 = 0;
+            for (const double *e : {e1, e2, e3})
+                emax2 = std::fmax(emax2, e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+            const double emax = std::sqrt(emax2), ext = 1e-6 * emax2 * emax / area2;
+            const double pad_t = std::fmax((double)pad, 4.0 * ext);
+            if (4.0 * ext < 0.25 * emax) // also false for NaN / zero-area
+            {
+                for (int a = 0; a < 3; ++a)
+                {
+                    p.lo[a] = std::fmin(v[a], std::fmin(v[3 + a], v[6 + a])) - (float)pad_t;
+                    p.hi[a] = std::fmax(v[a], std::fmax(v[3 + a], v[6 + a])) + (float)pad_t;
+                }
+                if (pad_t > (double)pad)
+                    ++out.n_sliver;
+            }
+            else
+            {
+                const float4 lo = out.ref_leaf_box[2 * leafOfTri[t]], hi = out.ref_leaf_box[2 * leafOfTri[t] + 1];
+                p.lo[0] = lo.x, p.lo[1] = lo.y, p.lo[2] = lo.z, p.hi[0] = hi.x, p.hi[1] = hi.y, p.hi[2] = hi.z;
+                ++out.n_needle;
+            }
+            for (int a = 0; a < 3; ++a)
+                p.c[a] = 0.5f * (p.lo[a] + p.hi[a]);
+            p.payload = t;
+            p.w = 1.0f;
+            prims.push_back(p);
+        }
+        if (prims.empty())
+            return "";
     }
+
+    WideBuilder wb{prims, leafMode ? 1 : 4, {}, {}};
+    wb.order.resize(prims.size());
+    for (size_t i = 0; i < prims.size(); ++i)
+        wb.order[i] = (int32_t)i;
+    wb.bn.reserve(prims.size() * 2);
+    wb.build(0, (int)prims.size());
     const std::vector<BNode> &bn = wb.bn;
+
+    // triangles of a binary leaf, appended to the fast arrays in leaf order; returns the leaf link
+    auto emitLeaf = [&](const BNode &c) -> int32_t {
+        const int32_t first = (int32_t)out.fast_orig.size();
+        for (int i = c.first; i < c.first + c.count; ++i)
+        {
+            const Prim &p = prims[wb.order[i]];
+            const int t0 = leafMode ? leaves[p.payload].first : p.payload;
+            const int cnt = leafMode ? leaves[p.payload].num : 1;
+            for (int t = t0; t < t0 + cnt; ++t)
+            {
+                out.fast_orig.push_back(t);
+                out.fast_geom.push_back(out.tri_geom[t]);
+                out.fast_key.push_back(out.tri_key[t]);
+                out.fast_rank.push_back(out.tri_rank[t]);
+                out.fast_leaf.push_back(leafOfTri[t]);
+            }
+        }
+        const int32_t count = (int32_t)out.fast_orig.size() - first;
+        return ~((first << 3) | (count - 1)); // count <= 8 in either mode
+    };
+
+    if (bn[0].right == -2)
+    {
+        // a single scan unit: no node, no box of this layout is ever tested
+        out.wide_root = emitLeaf(bn[0]);
+        return "";
+    }
 
     // collapse: a wide node adopts grandchildren, largest surface area first, until it has 4 children
     struct Item
@@ -374,7 +469,7 @@ std::string buildWide(const trt_scene_desc &desc, AccelBuild &out)
                 lo[a][k] = c.lo[a], hi[a][k] = c.hi[a];
             sah += halfArea(c.lo, c.hi) / rootArea;
             if (c.right == -2)
-                link[k] = prims[c.left].link;
+                link[k] = emitLeaf(c);
             else
             {
                 link[k] = (int32_t)out.wide_nodes.size();

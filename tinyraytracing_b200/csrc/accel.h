@@ -90,6 +90,14 @@ struct SceneView
     const WideNode *wide_nodes;
     int32_t wide_root;
     int32_t use_wide; // 0: the scene has no wide layout (too deep for its stack): reference-topology kernels only
+    // the fast layout's triangles in ITS leaf order: test data, tie key / rank, post-build index, and the reference
+    // leaf each triangle belongs to (a hit counts only if that leaf's box passes the reference's slab test)
+    const TriGeom *fast_geom;
+    const uint32_t *fast_key, *fast_rank;
+    const int32_t *fast_orig, *fast_leaf;
+    const float4 *ref_leaf_box; // 2 per reference leaf: (AA.xyz, -) (BB.xyz, -)
+    int32_t check_leaf_box;     // 0 only when the whole scene is ONE reference leaf (scanned without a box test)
+    float strict_origin_limit;  // rays starting farther than this from the coordinate origin take the strict walk
     int32_t n_tris;
     const TriGeom *tri_geom; // post-build order
     const uint32_t *tri_key; // tie key, higher wins at equal t
@@ -120,6 +128,14 @@ struct AccelBuild
     uint32_t miss_rank = 0;
     int32_t n_leaves = 0, ref_depth = 0;
     std::vector<WideNode> wide_nodes;
+    std::vector<TriGeom> fast_geom;
+    std::vector<uint32_t> fast_key, fast_rank;
+    std::vector<int32_t> fast_orig, fast_leaf;
+    std::vector<float4> ref_leaf_box;
+    bool root_is_reference_leaf = false;
+    float scene_scale = 0.f;
+    int32_t n_sliver = 0; // triangles whose box got the larger sliver pad
+    int32_t n_needle = 0; // triangles kept under their reference leaf's box
     int32_t wide_root = TRT_LINK_EMPTY, wide_depth = 0;
     double sah_ref = 0, sah_wide = 0; // expected box tests per random ray (surface-area heuristic), for the log
 };

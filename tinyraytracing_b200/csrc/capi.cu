@@ -197,8 +197,16 @@ int trt_scene_create(const trt_scene_desc *desc, int device, trt_scene **out)
     const std::string wide_err = buildWide(*desc, ab);
     v.use_wide = wide_err.empty() ? 1 : 0;
     v.wide_root = ab.wide_root;
-    if ((rc = upload(s.get(), ab.wide_nodes.data(), ab.wide_nodes.size(), &v.wide_nodes)))
+    if ((rc = upload(s.get(), ab.wide_nodes.data(), ab.wide_nodes.size(), &v.wide_nodes)) ||
+        (rc = upload(s.get(), ab.fast_geom.data(), ab.fast_geom.size(), &v.fast_geom)) ||
+        (rc = upload(s.get(), ab.fast_key.data(), ab.fast_key.size(), &v.fast_key)) ||
+        (rc = upload(s.get(), ab.fast_rank.data(), ab.fast_rank.size(), &v.fast_rank)) ||
+        (rc = upload(s.get(), ab.fast_orig.data(), ab.fast_orig.size(), &v.fast_orig)) ||
+        (rc = upload(s.get(), ab.fast_leaf.data(), ab.fast_leaf.size(), &v.fast_leaf)) ||
+        (rc = upload(s.get(), ab.ref_leaf_box.data(), ab.ref_leaf_box.size(), &v.ref_leaf_box)))
         return rc;
+    v.check_leaf_box = ab.root_is_reference_leaf ? 0 : 1;
+    v.strict_origin_limit = 4.0f * ab.scene_scale;
 
     std::vector<TriShade> shade(desc->n_tris);
     for (int i = 0; i < desc->n_tris; ++i)
@@ -278,6 +286,8 @@ int trt_scene_create(const trt_scene_desc *desc, int device, trt_scene **out)
     s->stats.accel_leaves = ab.n_leaves;
     s->stats.ref_depth = ab.ref_depth;
     s->stats.device = device;
+    s->stats.accel_slivers = ab.n_sliver;
+    s->stats.accel_needles = ab.n_needle;
     *out = s.release();
     return TRT_OK;
 }

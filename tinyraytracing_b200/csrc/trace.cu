@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_closest_counters(SceneView sv, 
         float3 S, d;
         loadRay(rays6, i, S, d);
         Hit hit;
-        if (!needsStrictWalk(S, d))
+        if (!needsStrictWalk(sv, S, d))
             traceWide<true>(sv, S, d, hit, &c);
     }
     uint32_t v[4] = {c.nodes, c.boxes, c.leaves, c.tris};

@@ -83,21 +83,49 @@ __device__ __forceinline__ bool triangleHit(const TriGeom &g, float3 S, float3 d
     return triangleInside(g.q0, g.q1, g.q2, S, d, t);
 }
 
+// Slab test of one child of a wide node: the reference's arithmetic ((B - S) * inv, un-fused).  For rays
+// admitted here every operand is finite and inv is finite and non-zero, so no NaN can appear and IEEE
+// fminf / fmaxf (one instruction) equal glm's compare-select min / max.
+__device__ __forceinline__ bool childPass(float3 S, float3 inv, float ax, float ay, float az, float bx, float by, float bz,
+                                          float &t0)
+{
+    const float inx = (bx - S.x) * inv.x, iny = (by - S.y) * inv.y, inz = (bz - S.z) * inv.z;
+    const float outx = (ax - S.x) * inv.x, outy = (ay - S.y) * inv.y, outz = (az - S.z) * inv.z;
+    const float t1 = fminf(fmaxf(inx, outx), fminf(fmaxf(iny, outy), fmaxf(inz, outz)));
+    t0 = fmaxf(fminf(inx, outx), fmaxf(fminf(iny, outy), fminf(inz, outz)));
+    return (t1 >= t0) && (((t0 > 0.0f) ? t0 : t1) > 0.0f);
+}
+
 // interactBVHNode (bvh.cpp:211-229) over one reference leaf, merged into the running best by (t, key).
 // One fused loop per lane.  Two alternatives were measured on staircase (4 Mi config-2 rays) and rejected:
 // splitting into a plane pass + an inside pass per lane (1.70 vs 2.13 Grays/s: the reloads and the recomputed
 // division cost more than the divergence they remove), and pooling the warp's candidates in shared memory
 // (walkPersistent<POOLED = true>, 1.93 Grays/s, latency-bound).
-__device__ __forceinline__ void scanLeaf(const SceneView &sv, int first, int num, float3 S, float3 d, Hit &hit)
+// FAST = false: triangles in post-build order (reference-topology walks; hit.id is the post-build index).
+// FAST = true: the fast layout's own leaf order; a candidate counts only if the REFERENCE leaf that holds the
+// triangle passes the reference's slab test for this ray (the reference never tests a triangle otherwise), and
+// hit.id is the fast index until the walk ends (toPostBuildId).
+template <bool FAST>
+__device__ __forceinline__ void scanLeaf(const SceneView &sv, int first, int num, float3 S, float3 d, float3 inv, Hit &hit)
 {
+    const TriGeom *geom = FAST ? sv.fast_geom : sv.tri_geom;
+    const uint32_t *keys = FAST ? sv.fast_key : sv.tri_key;
     for (int i = first; i < first + num; ++i)
     {
-        const float4 *gp = reinterpret_cast<const float4 *>(sv.tri_geom + i);
+        const float4 *gp = reinterpret_cast<const float4 *>(geom + i);
         TriGeom g;
         g.q0 = __ldg(gp), g.q1 = __ldg(gp + 1), g.q2 = __ldg(gp + 2);
         float t;
         if (triangleHit(g, S, d, hit.t, t))
         {
+            if (FAST && sv.check_leaf_box)
+            {
+                const float4 *bp = sv.ref_leaf_box + 2 * __ldg(sv.fast_leaf + i);
+                const float4 lo = __ldg(bp), hi = __ldg(bp + 1);
+                float t0;
+                if (!childPass(S, inv, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, t0))
+                    continue;
+            }
             if (t < hit.t)
             {
                 hit.t = t, hit.id = i, hit.key = 0xFFFFFFFFu; // key fetched lazily, only if a tie shows up
@@ -105,8 +133,8 @@ __device__ __forceinline__ void scanLeaf(const SceneView &sv, int first, int num
             else if (t == hit.t)
             {
                 if (hit.key == 0xFFFFFFFFu)
-                    hit.key = (hit.id < 0) ? TRT_MISS_KEY : __ldg(sv.tri_key + hit.id);
-                const uint32_t k = __ldg(sv.tri_key + i);
+                    hit.key = (hit.id < 0) ? TRT_MISS_KEY : __ldg(keys + hit.id);
+                const uint32_t k = __ldg(keys + i);
                 if (k > hit.key)
                     hit.id = i, hit.key = k;
             }
@@ -138,7 +166,7 @@ __device__ __forceinline__ void traceRefTopology(const SceneView &sv, float3 S, 
         if (cur < 0)
         {
             const int leaf = ~cur;
-            scanLeaf(sv, leaf >> 3, (leaf & 7) + 1, S, d, hit);
+            scanLeaf<false>(sv, leaf >> 3, (leaf & 7) + 1, S, d, inv, hit);
         }
         else
         {
@@ -184,32 +212,21 @@ __device__ __forceinline__ void traceRefTopology(const SceneView &sv, float3 S, 
 // ---- fast layout -------------------------------------------------------------------------------------------
 // Rays for which the slab test is not monotone in the box (a direction component that is exactly +-0 gives
 // inf*0 = NaN; non-finite origins / directions) take the reference's own exhaustive walk.
-__device__ __forceinline__ bool needsStrictWalk(float3 S, float3 d)
+__device__ __forceinline__ bool needsStrictWalk(const SceneView &sv, float3 S, float3 d)
 {
     // 1/d overflows to +-inf for zero AND for denormal components: test the reciprocal itself
     const float3 inv = rcpDir(d);
     const bool inf_rcp = !(fabsf(inv.x) <= 3.4028235e38f) || !(fabsf(inv.y) <= 3.4028235e38f) || !(fabsf(inv.z) <= 3.4028235e38f);
     const float sum = ((S.x + S.y) + S.z) + ((d.x + d.y) + d.z); // inf or NaN anywhere -> not finite
-    return inf_rcp || !(fabsf(sum) < 3.0e38f);
+    // far origins: the rounding of S + d*t grows with |S|, beyond what the fast layout's box pad was sized for
+    const bool far = fmaxf(fabsf(S.x), fmaxf(fabsf(S.y), fabsf(S.z))) > sv.strict_origin_limit;
+    return inf_rcp || far || !(fabsf(sum) < 3.0e38f);
 }
 
 struct TraceCounters
 {
     uint32_t nodes, boxes, leaves, tris;
 };
-
-// Slab test of one child of a wide node: the reference's arithmetic ((B - S) * inv, un-fused).  For rays
-// admitted here every operand is finite and inv is finite and non-zero, so no NaN can appear and IEEE
-// fminf / fmaxf (one instruction) equal glm's compare-select min / max.
-__device__ __forceinline__ bool childPass(float3 S, float3 inv, float ax, float ay, float az, float bx, float by, float bz,
-                                          float &t0)
-{
-    const float inx = (bx - S.x) * inv.x, iny = (by - S.y) * inv.y, inz = (bz - S.z) * inv.z;
-    const float outx = (ax - S.x) * inv.x, outy = (ay - S.y) * inv.y, outz = (az - S.z) * inv.z;
-    const float t1 = fminf(fmaxf(inx, outx), fminf(fmaxf(iny, outy), fmaxf(inz, outz)));
-    t0 = fmaxf(fminf(inx, outx), fmaxf(fminf(iny, outy), fminf(inz, outz)));
-    return (t1 >= t0) && (((t0 > 0.0f) ? t0 : t1) > 0.0f);
-}
 
 // 4-wide walk over the reference leaves: while-while (inner nodes until a leaf is reached, then the leaf scan),
 // nearest child first, entry-distance pruning at push and at pop.
@@ -282,11 +299,14 @@ __device__ __forceinline__ void traceWide(const SceneView &sv, float3 S, float3 
             cur = next;
         }
         if (cur == TRT_LINK_EXIT)
+        {
+            hit.id = (hit.id >= 0) ? __ldg(sv.fast_orig + hit.id) : -1; // fast index -> post-build index
             return;
+        }
         const int leaf = ~cur;
         if (STATS)
             cnt->leaves++, cnt->tris += (leaf & 7) + 1;
-        scanLeaf(sv, leaf >> 3, (leaf & 7) + 1, S, d, hit);
+        scanLeaf<true>(sv, leaf >> 3, (leaf & 7) + 1, S, d, inv, hit);
         do
         {
             --sp;
@@ -380,9 +400,17 @@ __device__ __forceinline__ void walkPoolInside(const SceneView &sv, const WalkSt
     const float3 d = f3(__shfl_sync(FULL, st.d.x, owner), __shfl_sync(FULL, st.d.y, owner), __shfl_sync(FULL, st.d.z, owner));
     if (valid)
     {
-        const float4 *gp = reinterpret_cast<const float4 *>(sv.tri_geom + tri);
-        if (triangleInside(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), S, d, t))
-            atomicMin(best + owner, ((unsigned long long)__float_as_uint(t) << 32) | __ldg(sv.tri_rank + tri));
+        const float4 *gp = reinterpret_cast<const float4 *>(sv.fast_geom + tri);
+        bool ok = triangleInside(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), S, d, t);
+        if (ok && sv.check_leaf_box)
+        {
+            const float4 *bp = sv.ref_leaf_box + 2 * __ldg(sv.fast_leaf + tri);
+            const float4 lo = __ldg(bp), hi = __ldg(bp + 1);
+            float t0;
+            ok = childPass(S, rcpDir(d), lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, t0);
+        }
+        if (ok)
+            atomicMin(best + owner, ((unsigned long long)__float_as_uint(t) << 32) | __ldg(sv.fast_rank + tri));
     }
 }
 
@@ -436,7 +464,7 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                     ray = mine;
                     rays.load(mine, st.S, st.d);
                     st.hit.t = TRT_INF, st.hit.id = -1, st.hit.key = 0xFFFFFFFFu;
-                    if (!sv.use_wide || needsStrictWalk(st.S, st.d))
+                    if (!sv.use_wide || needsStrictWalk(sv, st.S, st.d))
                     {
                         // rare: the reference's own walk, finished on the spot
                         if (sv.use_wide)
@@ -494,7 +522,7 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                 if (has)
                 {
                     const int lf = ~st.leaf;
-                    scanLeaf(sv, lf >> 3, (lf & 7) + 1, st.S, st.d, st.hit);
+                    scanLeaf<true>(sv, lf >> 3, (lf & 7) + 1, st.S, st.d, st.inv, st.hit);
                     if (st.cur < 0 && st.cur != TRT_LINK_EXIT)
                     {
                         st.leaf = st.cur; // a second leaf was reached while the first was postponed
@@ -515,7 +543,7 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                 float t = 0.f;
                 if (k < num)
                 {
-                    const float4 *gp = reinterpret_cast<const float4 *>(sv.tri_geom + first + k);
+                    const float4 *gp = reinterpret_cast<const float4 *>(sv.fast_geom + first + k);
                     cand = trianglePlane(__ldg(gp), __ldg(gp + 1), st.S, st.d, st.hit.t, t);
                 }
                 const unsigned m = __ballot_sync(FULL, cand);
@@ -562,6 +590,8 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                 st.hit.t = __uint_as_float((unsigned int)(b >> 32));
                 st.hit.id = __ldg(sv.rank_tri + (unsigned int)b);
             }
+            else
+                st.hit.id = (st.hit.id >= 0) ? __ldg(sv.fast_orig + st.hit.id) : -1;
             rays.store(ray, st.hit);
             ray = 0xffffffffu;
         }
@@ -574,7 +604,7 @@ __device__ __forceinline__ void traceClosest(const SceneView &sv, float3 S, floa
 {
     if (!sv.use_wide)
         traceRefTopology<false>(sv, S, d, hit);
-    else if (needsStrictWalk(S, d))
+    else if (needsStrictWalk(sv, S, d))
         traceRefTopology<true>(sv, S, d, hit);
     else
         traceWide<false>(sv, S, d, hit, nullptr);

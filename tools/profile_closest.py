@@ -44,5 +44,5 @@ with tempfile.TemporaryDirectory() as tmp:
     print("%s n=%d flags=%d: %.3f ms/launch, %.1f Mrays/s, hits %.3f" % (name, n, flags, ms, n / ms / 1e3,
                                                                          float((d_id >= 0).float().mean())))
     if flags == 0:
-        print("  traversal work per ray:", dev.trace_counters(rays[:: max(1, n >> 20)]), dev.stats()["accel_nodes"], "nodes")
+        print("  traversal work per ray:", dev.trace_counters(rays[:: max(1, n >> 20)]), {k: v for k, v in dev.stats().items() if k.startswith("accel")})
     dev.close()

@@ -2,14 +2,17 @@
 // tracer (wavefront.cu).  Replaces traverseBVH / interactAABB / interactBVHNode / interactTriangle
 // (bvh.cpp:146-245).  All arithmetic that decides a hit is un-fused IEEE float in the reference's order.
 //
-// Exactness argument: the reference walks EVERY child whose padded box passes interactAABB
-// and keeps the nearest hit with the tie rule of bvh.cpp:168-172,219.  That rule is a total order on
-// (t, key) with a per-triangle key computed at flatten time, so any visiting order gives the
-// reference's winner as long as every leaf whose own box passes is scanned unless it provably cannot win:
-//   * ancestor boxes contain descendant boxes exactly (min/max of the same floats) and the slab test is
-//     monotone in the box, so "leaf box passes" implies "all ancestors pass" — testing fewer or other
-//     enclosing boxes cannot add or lose leaves (rays with an exactly-zero direction component, where
-//     inf*0 = NaN breaks monotonicity, are routed to the exhaustive walk);
+// Exactness argument: the reference walks EVERY child whose padded box passes interactAABB and keeps
+// the nearest hit with the tie rule of bvh.cpp:168-172,219.  That rule is a total order on (t, key) with a
+// per-triangle key computed at flatten time, so any visiting order gives the reference's winner as long
+// as every triangle the reference tests is tested unless it provably cannot win, and no triangle it does NOT test is
+// ever reported:
+//   * a triangle is tested by the reference iff its leaf's box and all ancestor boxes pass; ancestor boxes contain
+//     descendant boxes exactly and the slab test is monotone in the box, so "leaf box passes" implies the rest
+//     (rays with a direction component whose reciprocal overflows, where inf*0 = NaN breaks monotonicity, and rays
+//     with non-finite or very distant origins are routed to the exhaustive walk of the reference topology);
+//   * the fast layout is its own tree over triangles: its boxes only cull (they contain every point at which
+//     interactTriangle can accept the triangle), and a candidate counts only if its REFERENCE leaf's box passes;
 //   * a subtree is skipped only when its entry distance exceeds the best t found so far.
 #pragma once
 #include "accel.h"
@@ -228,7 +231,7 @@ struct TraceCounters
     uint32_t nodes, boxes, leaves, tris;
 };
 
-// 4-wide walk over the reference leaves: while-while (inner nodes until a leaf is reached, then the leaf scan),
+// 4-wide walk of the fast layout: while-while (inner nodes until a leaf is reached, then the leaf scan),
 // nearest child first, entry-distance pruning at push and at pop.
 template <bool STATS>
 __device__ __forceinline__ void traceWide(const SceneView &sv, float3 S, float3 d, Hit &hit, TraceCounters *cnt)

@@ -308,6 +308,7 @@ def run_gpu(args):
                                "traffic": load_traffic(SCENE, n), "kernel": "k_closest_persistent",
                                "algorithmic_bytes_per_launch": bytes_per_ray * n, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
                                "bytes_per_ray": bytes_per_ray, "A": A, "T": T,
+                               "layout": layout_roofline(dev, rays, n, ms_res / args.steps, peak),
                                "note": "scene is L1/L2 resident (2 kB): the HBM-denominated figure is for cross-config comparison, SURVEY §8d"}
         if not args.no_render:
             out["render"] = render_measurements(args, tmp, rank, world, local, barrier)
@@ -325,6 +326,17 @@ def run_gpu(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def layout_roofline(dev, rays, n, ms_per_step, peak):
+    """The same figure with the bytes the DEFAULT traversal actually touches per ray (its own tree, counted on the
+    GPU by trt_trace_counters): 32 B ray I/O + 128 B per 4-wide node visited + 48 B per triangle tested.  The SURVEY
+    figure above is defined on the reference topology, so it exceeds what this layout moves."""
+    w = dev.trace_counters(rays[:: max(1, n >> 20)])
+    b = 32 + 128 * w["nodes"] + 48 * w["tris"]
+    achieved = b * n / (ms_per_step * 1e-3) / 1e9
+    return {"bytes_per_ray": b, "achieved": achieved, "frac": achieved / peak, "work_per_ray": w,
+            "note": "served from L1 (hit rate ~90 %): the kernel is issue / L1-latency bound, see profiles/"}
 
 
 def cpu_baseline(files, rays):

@@ -58,7 +58,7 @@ struct BatchRays
 };
 
 template <bool POOLED>
-__global__ void __launch_bounds__(kTraceBlock, 10) k_closest_persistent(SceneView sv, const float *__restrict__ rays6, unsigned int n,
+__global__ void __launch_bounds__(kTraceBlock) k_closest_persistent(SceneView sv, const float *__restrict__ rays6, unsigned int n,
                                                                     int32_t *__restrict__ out_id, float *__restrict__ out_t,
                                                                     unsigned int *counter)
 {

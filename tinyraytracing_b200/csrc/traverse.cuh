@@ -421,7 +421,7 @@ __device__ __forceinline__ void walkPoolInside(const SceneView &sv, const WalkSt
 // `counter` must be zero at launch; n = number of rays.  Every thread of the block must call this.
 // POOLED selects the leaf phase: false = every lane scans its own leaf (scanLeaf); true = the warp pools the
 // candidates that pass the plane test and deals their inside tests out one per lane (see below; measured in
-// profiles/r01_closest_staircase_pooled.txt: 8 % fewer instructions at 15 instead of 9.5 lanes, but the shorter
+// profiles/r01_closest_staircase_leaflayout_pooled.txt: 8 % fewer instructions at 15 instead of 9.5 lanes, but the shorter
 // dependent chains expose L1 latency — 69 % instead of 83 % issue-active — and it is 9 % slower, so it is off
 // by default and kept selectable (TRT_TRACE_POOLED) for the next round's latency work).
 template <bool POOLED, typename RAYS>

@@ -294,7 +294,11 @@ def run_gpu(args):
                        "l2": "inputs (%d MB rays + %d MB results per step) exceed the 126 MB L2" % (n * 24 >> 20, n * 8 >> 20),
                        "traversal": {0: "default", 2: "exhaustive", 4: "reftopo"}.get(args.flags, str(args.flags))},
             "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": n * 24 * world, "d2h_bytes_per_step": n * 8 * world,
-                    "ms_per_step": ms_e2e / args.steps, "timer": "host wall clock around the blocking C-ABI call"},
+                    "ms_per_step": ms_e2e / args.steps, "timer": "host wall clock around the blocking C-ABI call",
+                    "bound": "host link: %.1f GB/s H2D + %.1f GB/s D2H per GPU (24 B in, 8 B out per ray); the kernel itself "
+                             "needs %.1f %% of the step" % (n * 24 / (ms_e2e / args.steps * 1e-3) / 1e9,
+                                                           n * 8 / (ms_e2e / args.steps * 1e-3) / 1e9,
+                                                           100.0 * ms_res / ms_e2e)},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

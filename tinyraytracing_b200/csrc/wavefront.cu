@@ -331,20 +331,31 @@ __global__ void __launch_bounds__(kBlock) k_shade(SceneView sv, WfBuffers wf, in
                     double u0[2];
                     rng.block(4 + 2 * li, u0);
                     const double rnd = u0[0] * sv.first_light_area; // quirk A.5-1 (:38)
-                    // first light triangle whose cumulative area exceeds rnd (linear walk of :40-42 as a
-                    // binary search: the cumulative areas are non-decreasing)
-                    int lo = 0, hi = lt.n_tris;
+                    // first light triangle whose cumulative area exceeds rnd: the reference walks the list
+                    // linearly (:40-42).  rnd is drawn from [0, area of the FIRST light), so the answer is usually the
+                    // first triangle or none at all; otherwise gallop, then bisect (cumulative areas are non-decreasing)
                     const double *cum = sv.light_cum_area + lt.first_tri;
-                    while (lo < hi)
-                    {
-                        const int mid = (lo + hi) >> 1;
-                        if (rnd < cum[mid])
-                            hi = mid;
-                        else
-                            lo = mid + 1;
-                    }
-                    if (lo >= lt.n_tris)
+                    const int nt = lt.n_tris;
+                    if (nt == 0)
                         continue;
+                    int lo = 0;
+                    if (!(rnd < __ldg(cum)))
+                    {
+                        if (!(rnd < __ldg(cum + nt - 1)))
+                            continue; // no triangle selected: this light is not sampled at this vertex
+                        int a = 0, b = 1; // !(rnd < cum[a]); looking for the first b with rnd < cum[b]
+                        while (b < nt - 1 && !(rnd < __ldg(cum + b)))
+                            a = b, b = min(2 * b + 1, nt - 1);
+                        while (b - a > 1)
+                        {
+                            const int mid = (a + b) >> 1;
+                            if (rnd < __ldg(cum + mid))
+                                b = mid;
+                            else
+                                a = mid;
+                        }
+                        lo = b;
+                    }
                     double u1[2];
                     rng.block(5 + 2 * li, u1);
                     const double rnd1 = u0[1], rnd2 = u1[0], rnd3 = u1[1];

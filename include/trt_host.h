@@ -34,6 +34,10 @@ const char *trt_host_scene_material_name(trt_host_scene *s, int i);
 double trt_host_scene_build_seconds(trt_host_scene *s);
 void trt_host_scene_free(trt_host_scene *s);
 
+/* Baseline JPEG -> 8-bit BGR rows x cols x 3, bit-identical to cv::imread (what material.cpp:6 calls) on such
+ * files.  Call with bgr_out = NULL to get the size first. */
+int trt_decode_jpeg(const char *path, int32_t *rows, int32_t *cols, uint8_t *bgr_out, size_t capacity);
+
 /* Uncompressed 8-bit RGB(A) PNG, the role svpng.inc:77-108 plays in the reference (main.cpp:40). */
 int trt_write_png(const char *path, int32_t w, int32_t h, const uint8_t *rgb, int alpha);
 

@@ -63,7 +63,7 @@ EXPORTS = ["trt_device_count", "trt_scene_create", "trt_scene_destroy", "trt_hos
            "trt_render_accumulate", "trt_resolve", "trt_get_stats", "trt_reset_stats", "trt_last_error",
            "trt_version", "trt_host_scene_load", "trt_host_scene_from_arrays", "trt_host_scene_desc",
            "trt_host_scene_faces", "trt_host_scene_material_name", "trt_host_scene_build_seconds",
-           "trt_host_scene_free", "trt_write_png"]
+           "trt_host_scene_free", "trt_decode_jpeg", "trt_write_png"]
 
 
 def library_path():
@@ -115,6 +115,7 @@ def load_library():
     L.trt_host_scene_free.argtypes = [vp]
     L.trt_host_scene_free.restype = None
     L.trt_write_png.argtypes = [cp, i32, i32, vp, C.c_int]
+    L.trt_decode_jpeg.argtypes = [cp, C.POINTER(i32), C.POINTER(i32), vp, sz]
     _lib = L
     return L
 
@@ -129,6 +130,16 @@ def _np(ptr, shape, dtype):
     if n == 0 or not ptr:
         return np.zeros(shape, dtype)
     return np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype).reshape(shape).copy()
+
+
+def decode_jpeg(path):
+    """Baseline JPEG -> (rows, cols, 3) uint8 BGR with the library's own decoder (csrc/host/jpeg_decoder.cpp)."""
+    L = load_library()
+    r, c = C.c_int32(), C.c_int32()
+    _check(L.trt_decode_jpeg(path.encode(), C.byref(r), C.byref(c), None, 0), "trt_decode_jpeg")
+    out = np.empty((r.value, c.value, 3), np.uint8)
+    _check(L.trt_decode_jpeg(path.encode(), C.byref(r), C.byref(c), out.ctypes.data, out.size), "trt_decode_jpeg")
+    return out
 
 
 class HostScene:

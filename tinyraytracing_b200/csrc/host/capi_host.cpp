@@ -147,6 +147,34 @@ const char *trt_host_scene_material_name(trt_host_scene *s, int i)
 double trt_host_scene_build_seconds(trt_host_scene *s) { return s ? s->build_s : 0.0; }
 void trt_host_scene_free(trt_host_scene *s) { delete s; }
 
+int trt_decode_jpeg(const char *path, int32_t *rows, int32_t *cols, uint8_t *bgr_out, size_t capacity)
+{
+    if (!path || !rows || !cols)
+    {
+        trt::setLastError("trt_decode_jpeg: null argument");
+        return TRT_ERR_INVALID;
+    }
+    trt::Image img;
+    std::string why;
+    if (!trt::decodeJpegFile(path, img, why))
+    {
+        trt::setLastError("trt_decode_jpeg: " + why);
+        return TRT_ERR_INVALID;
+    }
+    *rows = img.rows, *cols = img.cols;
+    const size_t need = (size_t)img.rows * img.cols * 3;
+    if (bgr_out)
+    {
+        if (capacity < need)
+        {
+            trt::setLastError("trt_decode_jpeg: output buffer too small");
+            return TRT_ERR_LIMIT;
+        }
+        std::memcpy(bgr_out, img.data->data(), need);
+    }
+    return TRT_OK;
+}
+
 int trt_write_png(const char *path, int32_t w, int32_t h, const uint8_t *rgb, int alpha)
 {
     FILE *fp = std::fopen(path, "wb");

@@ -324,30 +324,37 @@ void Scene::readobj(std::string obj_path)
                 (int)nrm.size(), (int)uv.size(), (int)triangles.size());
 }
 
-// material.cpp:3-11 — the reference calls cv::imread; here the pre-decoded side-car is read instead.
+// material.cpp:3-11 — the reference calls cv::imread.  Baseline JPEG (all cg22 textures) is decoded here, bit for bit
+// as OpenCV's decoder does (jpeg_decoder.cpp); anything else is read from a pre-decoded side-car "<file>.bgr"
+// ("BGR8", int32 rows, int32 cols, bytes) written with cv2.imread by tinyraytracing_b200.scenes.write_bgr_sidecar.
 void Material::readinMap()
 {
     std::printf("Reading map_Kd file %s\n", map_Kd.c_str());
     img = Image();
-    if (FILE *f = std::fopen((map_Kd + ".bgr").c_str(), "rb"))
+    std::string why;
+    if (!decodeJpegFile(map_Kd, img, why))
     {
-        char magic[4];
-        int32_t rc[2];
-        if (std::fread(magic, 1, 4, f) == 4 && std::string(magic, 4) == "BGR8" && std::fread(rc, 4, 2, f) == 2 &&
-            rc[0] > 0 && rc[1] > 0)
+        img = Image();
+        if (FILE *f = std::fopen((map_Kd + ".bgr").c_str(), "rb"))
         {
-            auto buf = std::make_shared<std::vector<unsigned char>>((size_t)rc[0] * rc[1] * 3);
-            if (std::fread(buf->data(), 1, buf->size(), f) == buf->size())
+            char magic[4];
+            int32_t rc[2];
+            if (std::fread(magic, 1, 4, f) == 4 && std::string(magic, 4) == "BGR8" && std::fread(rc, 4, 2, f) == 2 &&
+                rc[0] > 0 && rc[1] > 0)
             {
-                img.data = buf;
-                img.rows = rc[0];
-                img.cols = rc[1];
+                auto buf = std::make_shared<std::vector<unsigned char>>((size_t)rc[0] * rc[1] * 3);
+                if (std::fread(buf->data(), 1, buf->size(), f) == buf->size())
+                {
+                    img.data = buf;
+                    img.rows = rc[0];
+                    img.cols = rc[1];
+                }
             }
+            std::fclose(f);
         }
-        std::fclose(f);
     }
     if (img.empty())
-        std::printf("Cannot read file: %s (expected pre-decoded side-car %s.bgr)\n", map_Kd.c_str(), map_Kd.c_str());
+        std::printf("Cannot read file: %s (%s; no side-car %s.bgr either)\n", map_Kd.c_str(), why.c_str(), map_Kd.c_str());
     map_height = img.rows;
     map_width = img.cols;
 }

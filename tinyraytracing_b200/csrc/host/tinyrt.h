@@ -67,10 +67,14 @@ struct Image
     bool empty() const { return !data || data->empty(); }
 };
 
+// Baseline JPEG -> 8-bit BGR (rows x cols x 3), bit-identical to OpenCV's cv::imread on such files (jpeg_decoder.cpp).
+bool decodeJpeg(const unsigned char *bytes, size_t n, Image &out, std::string &error);
+bool decodeJpegFile(const std::string &path, Image &out, std::string &error);
+
 class Material // material.h:11-33
 {
 public:
-    void readinMap(); // reads the "<map_Kd>.bgr" side-car (pre-decoded cv2.imread bytes)
+    void readinMap(); // decodes map_Kd (baseline JPEG) itself; other formats through a "<map_Kd>.bgr" side-car
     vec3 Kd, Ks, Tr;
     float Ns = 1, Ni = 1;
     std::string map_Kd;

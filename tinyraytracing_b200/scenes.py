@@ -6,9 +6,10 @@ does this framework's C++ host (csrc/host/scene.cpp).  /root/reference is not av
 equivalent text files: same statement order (so the `isvnvt` slot-order quirk of scene.cpp:149-153 is
 preserved), numbers printed with %.9g so every float32 round-trips exactly.
 
-Textures: the reference decodes JPEG with cv::imread (material.cpp:6).  There is no JPEG decoder on the
-C++ side here; `materialize` pre-decodes with Python cv2 (the same OpenCV decoder family, BGR order) into
-the side-car `<texture>.bgr` ("BGR8", int32 rows, int32 cols, bytes) that Material::readinMap reads.
+Textures: the reference decodes JPEG with cv::imread (material.cpp:6).  The C++ loader decodes baseline JPEG itself,
+bit-identically (csrc/host/jpeg_decoder.cpp); `materialize` also writes the cv2-decoded side-car `<texture>.bgr`
+("BGR8", int32 rows, int32 cols, bytes) that Material::readinMap falls back to for other formats, and that the
+oracle's shim imread uses.
 """
 import json
 import os

@@ -49,3 +49,15 @@ def test_trt_main_renders_the_scene_files(scene_files, device_scenes, tmp_path):
     img = device_scenes["back"].render(spp, seed=17)
     assert png.shape == img.shape
     assert np.array_equal(png, gamma_pack(img))
+
+
+@pytest.mark.parametrize("name", ("back", "staircase"))
+def test_cpp_host_surface_selftest(name, scene_files):
+    """csrc/host/selftest.cpp: the C++ classes and functions a reference user calls (Scene loaders, buildBVH,
+    traverseBVH -> HitRecord, the render loop) against the GPU-backed implementations."""
+    exe = os.path.join(ROOT, "tinyraytracing_b200", "bin", "trt_host_selftest")
+    assert os.path.exists(exe), "bin/trt_host_selftest not built"
+    f = scene_files[name]
+    r = subprocess.run([exe, f["basedir"], f["mtl"], f["xml"], f["obj"]], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and "host selftest ok" in r.stdout, r.stdout[-2000:]

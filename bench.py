@@ -385,7 +385,7 @@ def render_measurements(args, tmp, rank, world, local, barrier):
     from tinyraytracing_b200 import scenes
     from tinyraytracing_b200.distributed import render_on_gpus
 
-    cfgs = [("config3_veach_mis", "veach-mis", 1280, 720, args.spp3)]
+    cfgs = [("config1_cornell_shell", "back", 512, 512, 16), ("config3_veach_mis", "veach-mis", 1280, 720, args.spp3)]
     if world == 8 or args.config4:
         cfgs.append(("config4_staircase", "staircase", 1920, 1080, args.spp4))
     out = {}

@@ -2,7 +2,9 @@
 #include "accel.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <future>
 #include <cstdlib>
 #include <functional>
 
@@ -173,12 +175,12 @@ struct WideBuilder
     std::vector<Prim> &prims;
     int maxLeaf;
     std::vector<int32_t> order;
-    std::vector<BNode> bn;
+    std::vector<BNode> bn;         // pre-sized to 2 * prims: slots are handed out by `next`, so that the upper
+    std::atomic<int32_t> next{0};  // levels can build disjoint ranges on separate threads
 
-    int32_t build(int l, int r) // [l, r)
+    int32_t build(int l, int r, int depth = 0) // [l, r)
     {
-        const int32_t me = (int32_t)bn.size();
-        bn.emplace_back();
+        const int32_t me = next.fetch_add(1);
         float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
         float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
         for (int i = l; i < r; ++i)
@@ -256,8 +258,18 @@ struct WideBuilder
             if (mid == l || mid == r)
                 mid = (l + r) / 2;
         }
-        const int32_t L = build(l, mid);
-        const int32_t R = build(mid, r);
+        int32_t L, R;
+        if (depth < 6 && r - l >= (1 << 16))
+        {
+            auto left = std::async(std::launch::async, [this, l, mid, depth] { return build(l, mid, depth + 1); });
+            R = build(mid, r, depth + 1);
+            L = left.get();
+        }
+        else
+        {
+            L = build(l, mid, depth + 1);
+            R = build(mid, r, depth + 1);
+        }
         bn[me].left = L, bn[me].right = R;
         return me;
     }
@@ -388,7 +400,7 @@ std::string buildWide(const trt_scene_desc &desc, AccelBuild &out)
     wb.order.resize(prims.size());
     for (size_t i = 0; i < prims.size(); ++i)
         wb.order[i] = (int32_t)i;
-    wb.bn.reserve(prims.size() * 2);
+    wb.bn.resize(prims.size() * 2);
     wb.build(0, (int)prims.size());
     const std::vector<BNode> &bn = wb.bn;
 

@@ -20,6 +20,14 @@
 
 namespace trt
 {
+// 256-bit global load (LDG.E.256, sm_100): p must be 32-byte aligned
+__device__ __forceinline__ void ldg256(const void *p, float4 &a, float4 &b)
+{
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+
 struct Hit
 {
     float t;      // TRT_INF on miss
@@ -115,6 +123,7 @@ __device__ __forceinline__ void scanLeaf(const SceneView &sv, int first, int num
     const uint32_t *keys = FAST ? sv.fast_key : sv.tri_key;
     for (int i = first; i < first + num; ++i)
     {
+        // 48-byte records, three 128-bit loads (padding to 64 B for two 256-bit loads was measured: no gain)
         const float4 *gp = reinterpret_cast<const float4 *>(geom + i);
         TriGeom g;
         g.q0 = __ldg(gp), g.q1 = __ldg(gp + 1), g.q2 = __ldg(gp + 2);
@@ -226,6 +235,27 @@ __device__ __forceinline__ bool needsStrictWalk(const SceneView &sv, float3 S, f
     return inf_rcp || far || !(fabsf(sum) < 3.0e38f);
 }
 
+// A 128-byte wide node in four 256-bit loads (LDG.E.256, sm_100) instead of seven 128-bit ones: with every lane on
+// a different node the L1 data pipe pays one wavefront per lane per load instruction, and ncu shows that pipe at 73 %
+// of peak on staircase (profiles/r01_closest_staircase_default.txt).
+struct NodeRegs
+{
+    float4 lox, loy, loz, hix, hiy, hiz;
+    int4 lk;
+};
+__device__ __forceinline__ NodeRegs loadWideNode(const WideNode *n)
+{
+    NodeRegs r;
+    float4 l, pad;
+    const char *p = reinterpret_cast<const char *>(n);
+    ldg256(p, r.lox, r.loy);
+    ldg256(p + 32, r.loz, r.hix);
+    ldg256(p + 64, r.hiy, r.hiz);
+    ldg256(p + 96, l, pad);
+    r.lk = make_int4(__float_as_int(l.x), __float_as_int(l.y), __float_as_int(l.z), __float_as_int(l.w));
+    return r;
+}
+
 struct TraceCounters
 {
     uint32_t nodes, boxes, leaves, tris;
@@ -250,10 +280,9 @@ __device__ __forceinline__ void traceWide(const SceneView &sv, float3 S, float3 
     {
         while (cur >= 0)
         {
-            const float4 *np = reinterpret_cast<const float4 *>(sv.wide_nodes + cur);
-            const float4 lox = __ldg(np), loy = __ldg(np + 1), loz = __ldg(np + 2);
-            const float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
-            const int4 lk = __ldg(reinterpret_cast<const int4 *>(np + 6));
+            const NodeRegs nr = loadWideNode(sv.wide_nodes + cur);
+            const float4 lox = nr.lox, loy = nr.loy, loz = nr.loz, hix = nr.hix, hiy = nr.hiy, hiz = nr.hiz;
+            const int4 lk = nr.lk;
             float t0, t1, t2, t3;
             bool h0 = childPass(S, inv, lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, t0);
             bool h1 = childPass(S, inv, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, t1);
@@ -344,10 +373,9 @@ struct WalkState
 // One inner-node step of lane state `st` (st.cur >= 0 on entry).
 __device__ __forceinline__ void walkNodeStep(const SceneView &sv, WalkState &st, int32_t *stack_link, float *stack_t)
 {
-    const float4 *np = reinterpret_cast<const float4 *>(sv.wide_nodes + st.cur);
-    const float4 lox = __ldg(np), loy = __ldg(np + 1), loz = __ldg(np + 2);
-    const float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
-    const int4 lk = __ldg(reinterpret_cast<const int4 *>(np + 6));
+    const NodeRegs nr = loadWideNode(sv.wide_nodes + st.cur);
+    const float4 lox = nr.lox, loy = nr.loy, loz = nr.loz, hix = nr.hix, hiy = nr.hiy, hiz = nr.hiz;
+    const int4 lk = nr.lk;
     float t0, t1, t2, t3;
     bool h0 = childPass(st.S, st.inv, lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, t0);
     bool h1 = childPass(st.S, st.inv, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, t1);

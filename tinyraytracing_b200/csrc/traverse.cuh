@@ -256,6 +256,17 @@ __device__ __forceinline__ NodeRegs loadWideNode(const WideNode *n)
     return r;
 }
 
+// Traversal stack entry: (entry distance, link) packed in 64 bits, so that a push / pop is ONE local-memory access.
+// With every lane at its own stack depth each access costs a wavefront per lane in the L1 data pipe — the pipe that
+// bounds this kernel on staircase — so halving the stack instructions matters as much as the node loads.
+typedef unsigned long long StackEntry;
+__device__ __forceinline__ StackEntry packEntry(float t, int32_t link)
+{
+    return ((StackEntry)__float_as_uint(t) << 32) | (StackEntry)(uint32_t)link;
+}
+__device__ __forceinline__ float entryT(StackEntry e) { return __uint_as_float((uint32_t)(e >> 32)); }
+__device__ __forceinline__ int32_t entryLink(StackEntry e) { return (int32_t)(uint32_t)e; }
+
 struct TraceCounters
 {
     uint32_t nodes, boxes, leaves, tris;
@@ -270,10 +281,8 @@ __device__ __forceinline__ void traceWide(const SceneView &sv, float3 S, float3 
     if (sv.wide_root == TRT_LINK_EMPTY)
         return;
     const float3 inv = rcpDir(d);
-    int32_t stack_link[TRT_WIDE_STACK];
-    float stack_t[TRT_WIDE_STACK];
-    stack_link[0] = TRT_LINK_EXIT;
-    stack_t[0] = -1.f;
+    StackEntry stack[TRT_WIDE_STACK];
+    stack[0] = packEntry(-1.f, TRT_LINK_EXIT);
     int sp = 1;
     int32_t cur = sv.wide_root;
     for (;;)
@@ -314,19 +323,20 @@ __device__ __forceinline__ void traceWide(const SceneView &sv, float3 S, float3 
             const int nh = (int)h0 + (int)h1 + (int)h2 + (int)h3;
             if (nh == 0)
             {
+                StackEntry e;
                 do
                 {
-                    --sp;
-                    cur = stack_link[sp];
-                } while (stack_t[sp] > hit.t);
+                    e = stack[--sp];
+                } while (entryT(e) > hit.t);
+                cur = entryLink(e);
                 continue;
             }
             if (nh > 3)
-                stack_link[sp] = l3, stack_t[sp] = k3, ++sp;
+                stack[sp++] = packEntry(k3, l3);
             if (nh > 2)
-                stack_link[sp] = l2, stack_t[sp] = k2, ++sp;
+                stack[sp++] = packEntry(k2, l2);
             if (nh > 1)
-                stack_link[sp] = l1, stack_t[sp] = k1, ++sp;
+                stack[sp++] = packEntry(k1, l1);
             const int32_t next = l0;
             cur = next;
         }
@@ -339,11 +349,12 @@ __device__ __forceinline__ void traceWide(const SceneView &sv, float3 S, float3 
         if (STATS)
             cnt->leaves++, cnt->tris += (leaf & 7) + 1;
         scanLeaf<true>(sv, leaf >> 3, (leaf & 7) + 1, S, d, inv, hit);
+        StackEntry e;
         do
         {
-            --sp;
-            cur = stack_link[sp];
-        } while (stack_t[sp] > hit.t);
+            e = stack[--sp];
+        } while (entryT(e) > hit.t);
+        cur = entryLink(e);
     }
 }
 
@@ -363,15 +374,19 @@ struct WalkState
     int sp;
 };
 
-#define TRT_WALK_POP(st, stack_link, stack_t)                                                                        \
+#define TRT_WALK_POP(st, stack)                                                                                      \
     do                                                                                                              \
     {                                                                                                               \
-        --st.sp;                                                                                                    \
-        st.cur = stack_link[st.sp];                                                                                 \
-    } while (stack_t[st.sp] > st.hit.t)
+        StackEntry e__;                                                                                             \
+        do                                                                                                          \
+        {                                                                                                           \
+            e__ = stack[--st.sp];                                                                                   \
+        } while (entryT(e__) > st.hit.t);                                                                           \
+        st.cur = entryLink(e__);                                                                                    \
+    } while (0)
 
 // One inner-node step of lane state `st` (st.cur >= 0 on entry).
-__device__ __forceinline__ void walkNodeStep(const SceneView &sv, WalkState &st, int32_t *stack_link, float *stack_t)
+__device__ __forceinline__ void walkNodeStep(const SceneView &sv, WalkState &st, StackEntry *stack)
 {
     const NodeRegs nr = loadWideNode(sv.wide_nodes + st.cur);
     const float4 lox = nr.lox, loy = nr.loy, loz = nr.loz, hix = nr.hix, hiy = nr.hiy, hiz = nr.hiz;
@@ -403,15 +418,15 @@ __device__ __forceinline__ void walkNodeStep(const SceneView &sv, WalkState &st,
     const int nh = (int)h0 + (int)h1 + (int)h2 + (int)h3;
     if (nh == 0)
     {
-        TRT_WALK_POP(st, stack_link, stack_t);
+        TRT_WALK_POP(st, stack);
         return;
     }
     if (nh > 3)
-        stack_link[st.sp] = l3, stack_t[st.sp] = k3, ++st.sp;
+        stack[st.sp++] = packEntry(k3, l3);
     if (nh > 2)
-        stack_link[st.sp] = l2, stack_t[st.sp] = k2, ++st.sp;
+        stack[st.sp++] = packEntry(k2, l2);
     if (nh > 1)
-        stack_link[st.sp] = l1, stack_t[st.sp] = k1, ++st.sp;
+        stack[st.sp++] = packEntry(k1, l1);
     st.cur = l0;
 }
 
@@ -469,8 +484,7 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
     int32_t *pool_tri = s_pool_tri[warp], *pool_owner = s_pool_owner[warp];
     float *pool_t = s_pool_t[warp];
     unsigned long long *best = s_best[warp];
-    int32_t stack_link[TRT_WIDE_STACK];
-    float stack_t[TRT_WIDE_STACK];
+    StackEntry stack[TRT_WIDE_STACK];
     WalkState st;
     unsigned int ray = 0xffffffffu; // idle
     bool drained = false;           // the pool is empty
@@ -510,7 +524,7 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                         if (POOLED)
                             best[lane] = ((unsigned long long)__float_as_uint(TRT_INF) << 32) | sv.miss_rank;
                         st.inv = rcpDir(st.d);
-                        stack_link[0] = TRT_LINK_EXIT, stack_t[0] = -1.f;
+                        stack[0] = packEntry(-1.f, TRT_LINK_EXIT);
                         st.sp = 1;
                         st.cur = sv.wide_root;
                         st.leaf = TRT_LINK_EMPTY;
@@ -533,11 +547,11 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                 break;
             if (want)
             {
-                walkNodeStep(sv, st, stack_link, stack_t);
+                walkNodeStep(sv, st, stack);
                 if (st.cur < 0 && st.cur != TRT_LINK_EXIT && st.leaf == TRT_LINK_EMPTY)
                 {
                     st.leaf = st.cur; // postpone the leaf, keep walking
-                    TRT_WALK_POP(st, stack_link, stack_t);
+                    TRT_WALK_POP(st, stack);
                 }
             }
         }
@@ -557,7 +571,7 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                     if (st.cur < 0 && st.cur != TRT_LINK_EXIT)
                     {
                         st.leaf = st.cur; // a second leaf was reached while the first was postponed
-                        TRT_WALK_POP(st, stack_link, stack_t);
+                        TRT_WALK_POP(st, stack);
                     }
                     else
                         st.leaf = TRT_LINK_EMPTY;
@@ -606,7 +620,7 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                 if (st.cur < 0 && st.cur != TRT_LINK_EXIT)
                 {
                     st.leaf = st.cur; // a second leaf was reached while the first was postponed
-                    TRT_WALK_POP(st, stack_link, stack_t);
+                    TRT_WALK_POP(st, stack);
                 }
                 else
                     st.leaf = TRT_LINK_EMPTY;

@@ -70,15 +70,56 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region.  Polls NVML in-process from a thread (a query takes
+    well under a millisecond, so even a 10 ms timed region gets several samples); if NVML cannot be opened it falls
+    back to the `nvidia-smi -lms` loop of the B200_PROFILING.md recipe, whose first sample takes ~100 ms to arrive."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.nvml, self.handle, self.samples, self.run, self.keep = None, None, [], False, False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            handle = None
+            try:  # the CUDA ordinal is not the NVML index under CUDA_VISIBLE_DEVICES: go through the UUID
+                import torch
+
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+            self.nvml, self.handle = pynvml, handle
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        while self.run:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    why = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    why = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                if self.keep:
+                    self.samples.append((mhz, why))
+                else:
+                    self.last_before = (mhz, why)
+            except Exception:
+                pass
+            time.sleep(0.0005)
 
     def start(self):
+        if self.nvml:
+            self.run = True
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
@@ -91,8 +132,26 @@ class ClockSampler:
     def mark(self):
         """Samples before this point (warm-up) are dropped; if none arrives after it, the last one before is kept."""
         self.mark_at = len(self.lines)
+        self.keep = True
 
     def stop(self):
+        if self.nvml:
+            self.run = False
+            self.t.join(timeout=2)
+            nv = self.nvml
+            samples = self.samples or ([self.last_before] if hasattr(self, "last_before") else [])
+            bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            reasons = sorted(k for k, b in bits.items() if any(w & b for _, w in samples))
+            try:
+                mx = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            except Exception:
+                mx = None
+            sm = [float(m) for m, _ in samples]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": reasons,
+                    "samples": len(self.samples), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -119,7 +178,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 def materialize_scene(tmp):
@@ -399,12 +458,13 @@ def render_measurements(args, tmp, rank, world, local, barrier):
         finally:
             os.dup2(saved, 1)
         dev = trt.DeviceScene(host, local)
-        render_on_gpus(dev, spp, seed=2)  # warm-up at full size: allocates the wavefront buffers, primes NCCL
+        frame = dev.pinned_image()  # the frame lands in page-locked host memory (valid until dev.close())
+        render_on_gpus(dev, spp, seed=2, out=frame)  # warm-up at full size: allocates the wavefront buffers, primes NCCL
         barrier()
         dev.reset_stats()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        img = render_on_gpus(dev, spp, seed=1)
+        img = render_on_gpus(dev, spp, seed=1, out=frame)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)

@@ -297,9 +297,31 @@ class DeviceScene:
         return RenderParams(spp, sample_begin, spp if sample_end is None else sample_end, max_depth, seed,
                             batch_paths, flags)
 
-    def render(self, spp, seed=0, max_depth=0, sample_begin=0, sample_end=None, batch_paths=0, flags=0):
+    def pinned_image(self):
+        """A float64 (H, W, 3) array in page-locked host memory (trt_host_alloc), owned by this scene and reused:
+        pass it as `out=` to render / resolve so that the device-to-host copy of the frame is one DMA into memory
+        that is already mapped (a fresh pageable array costs a staged copy plus a page fault per 4 kB).  The array is
+        valid until close()."""
+        if getattr(self, "_pinned_img", None) is None:
+            n = self.height * self.width * 3
+            ptr = self.lib.trt_host_alloc(n * 8)
+            if not ptr:
+                raise TrtError("trt_host_alloc failed: " + self.lib.trt_last_error().decode())
+            self._pinned_ptr = ptr
+            self._pinned_img = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), (n,)).reshape(
+                self.height, self.width, 3)
+        return self._pinned_img
+
+    def _image_out(self, out):
+        if out is None:
+            return np.empty((self.height, self.width, 3), np.float64)
+        if out.dtype != np.float64 or out.shape != (self.height, self.width, 3) or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array of shape (H, W, 3)")
+        return out
+
+    def render(self, spp, seed=0, max_depth=0, sample_begin=0, sample_end=None, batch_paths=0, flags=0, out=None):
         """The reference's image buffer: float64 (H, W, 3), divided by spp."""
-        img = np.empty((self.height, self.width, 3), np.float64)
+        img = self._image_out(out)
         p = self.params(spp, sample_begin, sample_end, max_depth, seed, batch_paths, flags)
         _check(self.lib.trt_render(self.h, C.byref(p), img.ctypes.data), "trt_render")
         return img
@@ -307,8 +329,8 @@ class DeviceScene:
     def render_accumulate(self, params, d_accum_ptr, stream=0):
         _check(self.lib.trt_render_accumulate(self.h, C.byref(params), d_accum_ptr, stream), "trt_render_accumulate")
 
-    def resolve(self, d_accum_ptr, spp, want_rgb8=False, stream=0):
-        img = np.empty((self.height, self.width, 3), np.float64)
+    def resolve(self, d_accum_ptr, spp, want_rgb8=False, stream=0, out=None):
+        img = self._image_out(out)
         rgb = np.empty((self.height, self.width, 3), np.uint8) if want_rgb8 else None
         _check(self.lib.trt_resolve(self.h, d_accum_ptr, spp, img.ctypes.data,
                                     rgb.ctypes.data if want_rgb8 else None, stream), "trt_resolve")
@@ -326,6 +348,9 @@ class DeviceScene:
         if self.h:
             self.lib.trt_scene_destroy(self.h)
             self.h = None
+            if getattr(self, "_pinned_img", None) is not None:
+                self._pinned_img = None
+                self.lib.trt_host_free(self._pinned_ptr)
 
     def __del__(self):
         try:

@@ -85,6 +85,7 @@ trt_scene::~trt_scene()
     for (void *p : allocations)
         cudaFree(p);
     cudaFree(d_counter);
+    cudaFree(d_frame_image), cudaFree(d_frame_accum), cudaFree(d_frame_rgb8);
     for (int b = 0; b < 2; ++b)
     {
         if (stage_in[b])
@@ -477,26 +478,20 @@ int trt_resolve(trt_scene *s, const double *d_accum, int32_t spp, double *image_
     TRT_CUDA(cudaSetDevice(s->device));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const size_t n = (size_t)s->width * s->height * 3;
-    double *d_img = nullptr;
-    uint8_t *d_rgb = nullptr;
-    TRT_CUDA(cudaMalloc((void **)&d_img, n * sizeof(double)));
-    if (cudaMalloc((void **)&d_rgb, n) != cudaSuccess)
-    {
-        cudaFree(d_img);
-        return fail(TRT_ERR_CUDA, "cudaMalloc failed");
-    }
-    int rc = resolveImage(s, d_accum, spp, d_img, d_rgb, stream);
-    cudaError_t e = cudaSuccess;
-    if (rc == TRT_OK && image_rgb)
-        e = cudaMemcpyAsync(image_rgb, d_img, n * sizeof(double), cudaMemcpyDeviceToHost, stream);
-    if (rc == TRT_OK && e == cudaSuccess && rgb8)
-        e = cudaMemcpyAsync(rgb8, d_rgb, n, cudaMemcpyDeviceToHost, stream);
-    if (e == cudaSuccess)
-        e = cudaStreamSynchronize(stream);
-    cudaFree(d_img), cudaFree(d_rgb);
-    if (rc == TRT_OK && e != cudaSuccess)
-        return fail(TRT_ERR_CUDA, std::string("trt_resolve: ") + cudaGetErrorString(e));
-    return rc;
+    if (!s->d_frame_image)
+        TRT_CUDA(cudaMalloc((void **)&s->d_frame_image, n * sizeof(double)));
+    if (!s->d_frame_rgb8)
+        TRT_CUDA(cudaMalloc((void **)&s->d_frame_rgb8, n));
+    int rc = resolveImage(s, d_accum, spp, s->d_frame_image, s->d_frame_rgb8, stream);
+    if (rc != TRT_OK)
+        return rc;
+    // pinned destinations (trt_host_alloc) are written by the copy engine directly; pageable ones are staged by the driver
+    if (image_rgb)
+        TRT_CUDA(cudaMemcpyAsync(image_rgb, s->d_frame_image, n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (rgb8)
+        TRT_CUDA(cudaMemcpyAsync(rgb8, s->d_frame_rgb8, n, cudaMemcpyDeviceToHost, stream));
+    TRT_CUDA(cudaStreamSynchronize(stream));
+    return TRT_OK;
 }
 
 int trt_render(trt_scene *s, const trt_render_params *p, double *image_rgb)
@@ -505,16 +500,12 @@ int trt_render(trt_scene *s, const trt_render_params *p, double *image_rgb)
         return fail(TRT_ERR_INVALID, "trt_render: null argument");
     TRT_CUDA(cudaSetDevice(s->device));
     const size_t n = (size_t)s->width * s->height * 3;
-    double *d_accum = nullptr;
-    TRT_CUDA(cudaMalloc((void **)&d_accum, n * sizeof(double)));
-    int rc = TRT_OK;
-    if (cudaMemsetAsync(d_accum, 0, n * sizeof(double), s->stream) != cudaSuccess)
-        rc = fail(TRT_ERR_CUDA, "cudaMemsetAsync failed");
+    if (!s->d_frame_accum)
+        TRT_CUDA(cudaMalloc((void **)&s->d_frame_accum, n * sizeof(double)));
+    TRT_CUDA(cudaMemsetAsync(s->d_frame_accum, 0, n * sizeof(double), s->stream));
+    int rc = trt_render_accumulate(s, p, s->d_frame_accum, s->stream);
     if (rc == TRT_OK)
-        rc = trt_render_accumulate(s, p, d_accum, s->stream);
-    if (rc == TRT_OK)
-        rc = trt_resolve(s, d_accum, p->spp, image_rgb, nullptr, s->stream);
-    cudaFree(d_accum);
+        rc = trt_resolve(s, s->d_frame_accum, p->spp, image_rgb, nullptr, s->stream);
     return rc;
 }
 

@@ -46,6 +46,10 @@ struct trt_scene
     unsigned int *d_counter = nullptr; // ray-pool counters of the persistent kernels
     int persistent_blocks_per_sm = 1, pooled_blocks_per_sm = 1;
     trt::Wavefront *wf = nullptr;
+    // frame buffers of trt_resolve / trt_render, allocated on first use and kept: a cudaMalloc / cudaFree pair per
+    // call synchronises the device and costs more than the resolve kernel itself on small frames
+    double *d_frame_image = nullptr, *d_frame_accum = nullptr;
+    uint8_t *d_frame_rgb8 = nullptr;
     trt_stats stats{};
     int width = 0, height = 0;
 };

@@ -31,8 +31,9 @@ def render_distributed(accumulate, resolve, shape, spp, device=None, group=None,
     return resolve(acc) if rank == dst else None
 
 
-def render_on_gpus(dev, spp, seed=0, max_depth=0, group=None):
-    """The reference's image (float64 H x W x 3, divided by spp) on rank 0, rendered by all ranks' GPUs."""
+def render_on_gpus(dev, spp, seed=0, max_depth=0, group=None, out=None):
+    """The reference's image (float64 H x W x 3, divided by spp) on rank 0, rendered by all ranks' GPUs.
+    out: optional destination array (e.g. dev.pinned_image()), see DeviceScene.resolve."""
     import torch
 
     stream = torch.cuda.current_stream().cuda_stream
@@ -41,7 +42,7 @@ def render_on_gpus(dev, spp, seed=0, max_depth=0, group=None):
         dev.render_accumulate(dev.params(spp, lo, hi, max_depth=max_depth, seed=seed), acc.data_ptr(), stream)
 
     def resolve(acc):
-        return dev.resolve(acc.data_ptr(), spp, stream=stream)
+        return dev.resolve(acc.data_ptr(), spp, stream=stream, out=out)
 
     return render_distributed(accumulate, resolve, (dev.height, dev.width, 3), spp,
                               device=torch.device("cuda", torch.cuda.current_device()), group=group)

@@ -154,6 +154,7 @@ typedef struct trt_render_params {
 
 #define TRT_RENDER_REFTOPO 1u /* trace with the reference-topology kernel instead of the fast layout */
 #define TRT_RENDER_PLAIN 2u   /* fast layout, plain thread-per-ray traversal instead of the persistent walker */
+#define TRT_RENDER_PROFILE 4u /* time each kernel class with CUDA events (trt_stats.ms_*); the image is unchanged */
 
 /* Renders the sample range and writes the reference's image buffer: double[H*W*3], row-major RGB, rows
  * top to bottom, already divided by spp (main.cpp:74,101-108) — what imshow (main.cpp:19-42) consumes. */
@@ -184,6 +185,9 @@ typedef struct trt_stats {
     int32_t device;
     int32_t accel_slivers; /* triangles boxed with the larger sliver pad (fast layout)                    */
     int32_t accel_needles; /* triangles left under their reference leaf's box (fast layout)               */
+    /* device time per kernel class of the last render made with TRT_RENDER_PROFILE (CUDA events between the launches;
+       the role the clock() prints of main.cpp:60-61,116-117 play in the reference), else 0 */
+    double ms_trace, ms_shade, ms_shadow, ms_accumulate;
 } trt_stats;
 
 int trt_get_stats(trt_scene *scene, trt_stats *out);

@@ -100,3 +100,35 @@ def test_render_agrees_with_reference_statistically(name, device_scenes):
     floor = np.sqrt(((c1 - c2) ** 2).mean())
     assert np.sqrt(((cg - c1) ** 2).mean()) <= 1.25 * floor
     assert np.sqrt(((cg - c2) ** 2).mean()) <= 1.25 * floor
+
+
+def test_profile_flag_times_kernel_classes_without_changing_the_image(device_scenes):
+    """TRT_RENDER_PROFILE: CUDA-event time per kernel class (the role of main.cpp:60-61,116-117's clock() prints);
+    the image is bit-identical and the class times add up to no more than the render's own device time."""
+    from tinyraytracing_b200.api import RENDER_PROFILE
+
+    dev = device_scenes["veach-mis"]
+    plain = dev.render(4, seed=9)
+    assert dev.stats()["ms_shade"] == 0.0
+    prof = dev.render(4, seed=9, flags=RENDER_PROFILE)
+    assert np.array_equal(plain, prof)
+    st = dev.stats()
+    parts = [st[k] for k in ("ms_trace", "ms_shade", "ms_shadow", "ms_accumulate")]
+    assert all(p > 0 for p in parts)
+    assert sum(parts) <= st["last_render_ms"] * 1.001
+
+
+def test_render_into_pinned_frame(device_scenes):
+    """out=: the frame is written into a caller-supplied (H, W, 3) float64 array; the scene's page-locked frame
+    (trt_host_alloc) is reused across renders and holds the same image as a fresh pageable array."""
+    dev = device_scenes["back"]
+    fresh = dev.render(2, seed=3)
+    frame = dev.pinned_image()
+    assert frame.shape == fresh.shape and frame.dtype == np.float64
+    got = dev.render(2, seed=3, out=frame)
+    assert got is frame and np.array_equal(frame, fresh)
+    assert dev.pinned_image() is frame
+    with pytest.raises(ValueError):
+        dev.render(2, seed=3, out=np.empty((dev.height, dev.width, 3), np.float32))
+    with pytest.raises(ValueError):
+        dev.render(2, seed=3, out=np.empty((dev.height + 1, dev.width, 3), np.float64))

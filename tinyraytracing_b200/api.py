@@ -12,6 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 INF = np.float32(114514.0)
 TRACE_DEVICE_PTRS, TRACE_EXHAUSTIVE, TRACE_REFTOPO, TRACE_PLAIN, TRACE_POOLED = 1, 2, 4, 8, 16
 RENDER_REFTOPO = 1
+RENDER_PLAIN = 2
+RENDER_PROFILE = 4
 
 
 class TrtError(RuntimeError):
@@ -54,7 +56,9 @@ class Stats(C.Structure):
     _fields_ = [("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64), ("paths", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("last_render_ms", C.c_double), ("last_trace_ms", C.c_double),
                 ("accel_nodes", C.c_int32), ("accel_leaves", C.c_int32), ("ref_depth", C.c_int32),
-                ("device", C.c_int32), ("accel_slivers", C.c_int32), ("accel_needles", C.c_int32)]
+                ("device", C.c_int32), ("accel_slivers", C.c_int32), ("accel_needles", C.c_int32),
+                ("ms_trace", C.c_double), ("ms_shade", C.c_double), ("ms_shadow", C.c_double),
+                ("ms_accumulate", C.c_double)]
 
 
 # every symbol include/trt.h and include/trt_host.h declare (tests check the library exports all of them)

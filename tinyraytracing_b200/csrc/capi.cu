@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <memory>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 

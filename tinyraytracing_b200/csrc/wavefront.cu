@@ -31,6 +31,12 @@ namespace trt
 namespace
 {
 constexpr int kBlock = 128;
+// k_shade is bound by registers (112 unconstrained) and insensitive to its instruction count (ncu + A/B):
+// 64-thread CTAs with at least 9 resident per SM cap it at 96 registers (48 bytes of spills) = 5 warps per scheduler
+// instead of 4 — the register file is partitioned per scheduler, so 112 registers give 4 warps whatever the CTA size.
+// Measured against 128 threads / 112 registers (k_shade's own device time, TRT_RENDER_PROFILE): back 2.73 -> 2.66 ms,
+// veach-mis 22.4 -> 21.4 ms, staircase 32.2 -> 30.9 ms.
+constexpr int kShadeBlock = 64, kShadeMinBlocks = 9;
 constexpr int kMaxLights = 32;
 constexpr float kPI = 3.1415926f; // pathtracing.h:11
 constexpr float kPRR = 0.8f;      // pathtracing.h:12
@@ -100,6 +106,20 @@ struct Rng
 };
 
 __device__ __forceinline__ float3 xyz(float4 v) { return f3(v.x, v.y, v.z); }
+
+// IEEE x / c for a finite c > 0, bit for bit, without the division's slow path on a zero dividend: FCHK sends
+// 0 / c to a ~100-instruction subroutine (ncu, profiles/r01_render_shade_staircase.txt: 11 % of k_shade's warp
+// instructions were that subroutine, fed by Ks = 0 and by colours with a zero channel).  +-0 / c = +-0 = x.
+__device__ __forceinline__ float divByPositive(float x, float c)
+{
+    const bool zero = (x == 0.f);
+    const float q = (zero ? 1.0f : x) / c;
+    return zero ? x : q;
+}
+__device__ __forceinline__ float3 divByPositive(float3 v, float c)
+{
+    return f3(divByPositive(v.x, c), divByPositive(v.y, c), divByPositive(v.z, c));
+}
 __device__ __forceinline__ float4 xyzw(float3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
 
 // ------------------------------------------------------------------------------------------------ K1
@@ -266,7 +286,7 @@ __device__ __forceinline__ void appendQueue(int32_t *counter, int32_t *queue, bo
         queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
 }
 
-__global__ void __launch_bounds__(kBlock) k_shade(SceneView sv, WfBuffers wf, int qsel, int depth, int max_depth,
+__global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) k_shade(SceneView sv, WfBuffers wf, int qsel, int depth, int max_depth,
                                                   int sample0, uint64_t seed)
 {
   const int count = wf.counters[qsel];
@@ -288,8 +308,10 @@ __global__ void __launch_bounds__(kBlock) k_shade(SceneView sv, WfBuffers wf, in
         if (tri >= 0)
         {
             const TriShade ts = sv.tri_shade[tri];
-            const DeviceMaterial m = sv.materials[ts.mtl];
-            if (m.is_emissive)
+            // material fields are fetched where they are used (L1-resident table) instead of holding the whole record
+            // in registers across the light loop: k_shade's occupancy is register-bound
+            const DeviceMaterial *mp = sv.materials + ts.mtl;
+            if (mp->is_emissive)
             {
                 // :9-12 returns the radiance; DIFFUSE / SPECULAR arrivals drop it (:87-94), camera and
                 // TRANSMISSION arrivals keep it (main.cpp:101, :95-96)
@@ -297,7 +319,8 @@ __global__ void __launch_bounds__(kBlock) k_shade(SceneView sv, WfBuffers wf, in
                 {
                     const float4 T = wf.thr[slot];
                     float4 L = wf.L[slot];
-                    L.x += T.x * m.radiance.x, L.y += T.y * m.radiance.y, L.z += T.z * m.radiance.z;
+                    const float3 rad = mp->radiance;
+                    L.x += T.x * rad.x, L.y += T.y * rad.y, L.z += T.z * rad.z;
                     wf.L[slot] = L;
                 }
             }
@@ -312,13 +335,16 @@ __global__ void __launch_bounds__(kBlock) k_shade(SceneView sv, WfBuffers wf, in
                 float bx, by, bz;
                 baryLeastSquares(sv.tri_v + (size_t)tri * 9, P, bx, by, bz);
                 const float3 pn = shadingNormal(ts.vn, bx, by, bz); // bvh.cpp:223-224
-                float3 Kd = m.Kd;
-                if (m.texture >= 0) // :17-26
+                float3 Kd = mp->Kd;
+                const int m_texture = mp->texture;
+                const float3 m_Ks = mp->Ks;
+                const float m_Ns = mp->Ns;
+                if (m_texture >= 0) // :17-26
                 {
                     const double col = (ts.vt[0] * bx + ts.vt[2] * by) + ts.vt[4] * bz;
                     const double row = (ts.vt[1] * bx + ts.vt[3] * by) + ts.vt[5] * bz;
                     const double irow = row - floor(row), icol = col - floor(col);
-                    const DeviceTexture tx = sv.textures[m.texture];
+                    const DeviceTexture tx = sv.textures[m_texture];
                     const int r = (int)(irow * tx.rows), c = (int)(icol * tx.cols);
                     const uint8_t *px = tx.bgr + ((size_t)r * tx.cols + c) * 3;
                     Kd = f3((float)((double)px[2] / 255), (float)((double)px[1] / 255), (float)((double)px[0] / 255));
@@ -381,9 +407,12 @@ __global__ void __launch_bounds__(kBlock) k_shade(SceneView sv, WfBuffers wf, in
                     const double cos_alpha = fmax((double)dot3(pn, h), 0.0);
                     // Ks == 0 (every diffuse material): Ks * (Ns+2) * pow(...) is +0 for any finite power, and the
                     // power is finite for cos_alpha in [0,1] and Ns >= 0 — the double-precision pow is skipped
-                    const bool no_spec = (m.Ks.x == 0.f) && (m.Ks.y == 0.f) && (m.Ks.z == 0.f) && (m.Ns >= 0.f);
-                    const float spec = no_spec ? 0.f : (float)pow(cos_alpha, (double)m.Ns);
-                    const float3 brdf = (Kd / kPI) + (((m.Ks * (m.Ns + 2.0f)) * spec) / (2.0f * kPI));
+                    const bool no_spec = (m_Ks.x == 0.f) && (m_Ks.y == 0.f) && (m_Ks.z == 0.f) && (m_Ns >= 0.f);
+                    // the specular term of a diffuse material is (+0 * (Ns + 2)) * 0 / 2pi = +0 in every channel
+                    float3 spec_term = f3(0.f, 0.f, 0.f);
+                    if (!no_spec)
+                        spec_term = divByPositive((m_Ks * (m_Ns + 2.0f)) * (float)pow(cos_alpha, (double)m_Ns), 2.0f * kPI);
+                    const float3 brdf = divByPositive(Kd, kPI) + spec_term;
                     const float3 contrib = intensity * brdf;
                     const int cidx = slot * sv.n_lights + li;
                     wf.sh_contrib[cidx] = xyzw(contrib, 0.f);
@@ -413,15 +442,16 @@ __global__ void __launch_bounds__(kBlock) k_shade(SceneView sv, WfBuffers wf, in
                     int type = INVALID;
                     float3 ndir = f3(0.f, 0.f, 0.f);
                     bool decided = false;
-                    if (m.Ni > 1.f)
+                    const float m_Ni = mp->Ni;
+                    if (m_Ni > 1.f)
                     {
                         double n1, n2;
                         const double cos_in = (double)dot3(ray_direction, pn);
                         float3 normal;
                         if (cos_in > 0)
-                            normal = -pn, n1 = (double)m.Ni, n2 = 1.0;
+                            normal = -pn, n1 = (double)m_Ni, n2 = 1.0;
                         else
-                            normal = pn, n1 = 1.0, n2 = (double)m.Ni;
+                            normal = pn, n1 = 1.0, n2 = (double)m_Ni;
                         const double q = (n1 - n2) / (n1 + n2);
                         const double rf0 = q * q;
                         const double a = (double)1.0f - fabs(cos_in);
@@ -442,7 +472,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(SceneView sv, WfBuffers wf, in
                     }
                     if (!decided)
                     {
-                        const double Kd_len = (double)length3(m.Kd), Ks_len = (double)length3(m.Ks);
+                        const double Kd_len = (double)length3(mp->Kd), Ks_len = (double)length3(m_Ks);
                         const double kd = Kd_len / (Kd_len + Ks_len), ks = Ks_len / (Kd_len + Ks_len);
                         double ul[2], ut[2];
                         rng.block(2, ul);
@@ -450,20 +480,20 @@ __global__ void __launch_bounds__(kBlock) k_shade(SceneView sv, WfBuffers wf, in
                         if (p < kd)
                         {
                             rng.block(3, ut);
-                            ndir = sampleLobe(pn, DIFFUSE, (double)m.Ns, ul[1], ut[0]);
+                            ndir = sampleLobe(pn, DIFFUSE, (double)m_Ns, ul[1], ut[0]);
                             type = DIFFUSE;
                         }
-                        else if (m.Ns > 1.f && p < kd + ks)
+                        else if (m_Ns > 1.f && p < kd + ks)
                         {
                             rng.block(3, ut);
-                            ndir = sampleLobe(reflect3(ray_direction, pn), SPECULAR, (double)m.Ns, ul[1], ut[0]);
+                            ndir = sampleLobe(reflect3(ray_direction, pn), SPECULAR, (double)m_Ns, ul[1], ut[0]);
                             type = SPECULAR;
                         }
                     }
                     if (type != INVALID) // the reference traces the INVALID ray too and discards it (:81-82)
                     {
-                        const float3 w = (type == TRANSMISSION) ? m.Tr : Kd; // SPECULAR also weights by Kd (:92-93)
-                        weight = xyzw(w / kPRR, 0.f);
+                        const float3 w = (type == TRANSMISSION) ? mp->Tr : Kd; // SPECULAR also weights by Kd (:92-93)
+                        weight = xyzw(divByPositive(w, kPRR), 0.f);
                         wf.ray_o[slot] = xyzw(P, 0.f);
                         wf.ray_d[slot] = xyzw(ndir, __int_as_float(type));
                         survives = true;
@@ -560,7 +590,8 @@ struct Wavefront
     int32_t *h_ring = nullptr; // pinned: kRing snapshots of the device counters
     cudaEvent_t ring_ev[kRing] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int blocks_trace = 1, blocks_shadow = 1;
+    int blocks_trace = 1, blocks_shadow = 1, blocks_shade = 1;
+    std::vector<cudaEvent_t> prof_ev; // TRT_RENDER_PROFILE: five timestamps per iteration, grown on demand
 };
 
 void destroyWavefront(trt_scene *s)
@@ -576,6 +607,8 @@ void destroyWavefront(trt_scene *s)
             cudaEventDestroy(e);
     if (s->wf->ev0)
         cudaEventDestroy(s->wf->ev0), cudaEventDestroy(s->wf->ev1);
+    for (cudaEvent_t e : s->wf->prof_ev)
+        cudaEventDestroy(e);
     delete s->wf;
     s->wf = nullptr;
 }
@@ -615,6 +648,7 @@ static int ensureWavefront(trt_scene *s, int paths)
     TRT_CUDA(cudaEventCreate(&w->ev1));
     TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w->blocks_trace, k_trace<0>, kBlock, 0));
     TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w->blocks_shadow, k_shadow<0>, kBlock, 0));
+    TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w->blocks_shade, k_shade, kShadeBlock, 0));
     return TRT_OK;
 }
 
@@ -663,6 +697,22 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
     const unsigned grid_trace = (unsigned)(s->sm_count * std::max(1, w->blocks_trace));
     const unsigned grid_shadow = (unsigned)(s->sm_count * std::max(1, w->blocks_shadow));
     const unsigned grid_shade = (unsigned)(s->sm_count * 8);
+    // k_shade: exactly the resident CTAs (grid-stride loop inside): a second, partly filled wave of CTAs would cost a
+    // whole extra pass of ~40 us warp iterations
+    const unsigned grid_kshade = (unsigned)(s->sm_count * std::max(1, w->blocks_shade));
+    const bool profile = (p.flags & TRT_RENDER_PROFILE) != 0;
+    size_t prof_used = 0;
+    double prof_ms[4] = {0, 0, 0, 0};
+    auto stamp = [&]() -> int { // a timestamp on the stream between two launches
+        if (prof_used == w->prof_ev.size())
+        {
+            cudaEvent_t e;
+            TRT_CUDA(cudaEventCreate(&e));
+            w->prof_ev.push_back(e);
+        }
+        TRT_CUDA(cudaEventRecord(w->prof_ev[prof_used++], stream));
+        return TRT_OK;
+    };
     TRT_CUDA(cudaEventRecord(w->ev0, stream));
     for (int s0 = p.sample_begin; s0 < p.sample_end; s0 += spb)
     {
@@ -691,24 +741,34 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
         for (; !dead; ++depth)
         {
             const unsigned grid_plain = (unsigned)(s->sm_count * 16);
+            if (profile && (rc = stamp()))
+                return rc;
             if (mode == 1)
                 k_trace<1><<<grid_plain, kBlock, 0, stream>>>(s->view, b, q);
             else if (mode == 2)
                 k_trace<2><<<grid_plain, kBlock, 0, stream>>>(s->view, b, q);
             else
                 k_trace<0><<<grid_trace, kBlock, 0, stream>>>(s->view, b, q);
+            if (profile && (rc = stamp()))
+                return rc;
             k_reset_counters<<<1, 32, 0, stream>>>(b, q ^ 1);
-            k_shade<<<grid_shade, kBlock, 0, stream>>>(s->view, b, q, depth, p.max_depth, s0, p.seed);
+            k_shade<<<grid_kshade, kShadeBlock, 0, stream>>>(s->view, b, q, depth, p.max_depth, s0, p.seed);
             TRT_CUDA(cudaMemcpyAsync(w->h_ring + (size_t)(depth % Wavefront::kRing) * kNumCounters, b.counters,
                                      kNumCounters * 4, cudaMemcpyDeviceToHost, stream));
             TRT_CUDA(cudaEventRecord(w->ring_ev[depth % Wavefront::kRing], stream));
+            if (profile && (rc = stamp()))
+                return rc;
             if (mode == 1)
                 k_shadow<1><<<grid_plain, kBlock, 0, stream>>>(s->view, b);
             else if (mode == 2)
                 k_shadow<2><<<grid_plain, kBlock, 0, stream>>>(s->view, b);
             else
                 k_shadow<0><<<grid_shadow, kBlock, 0, stream>>>(s->view, b);
+            if (profile && (rc = stamp()))
+                return rc;
             k_accumulate<<<grid_shade, kBlock, 0, stream>>>(s->view, b, q);
+            if (profile && (rc = stamp()))
+                return rc;
             s->stats.kernel_launches += 5;
             q ^= 1;
             if (depth >= kLag && (rc = consume(consumed++)))
@@ -718,6 +778,19 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
         for (; consumed < depth; ++consumed)
             if ((rc = consume(consumed)))
                 return rc;
+        if (profile)
+        {
+            // five timestamps per iteration: trace | reset + shade + counter snapshot | shadow | accumulate
+            TRT_CUDA(cudaStreamSynchronize(stream));
+            for (size_t i = 0; i + 4 < prof_used; i += 5)
+                for (int k = 0; k < 4; ++k)
+                {
+                    float ms = 0;
+                    TRT_CUDA(cudaEventElapsedTime(&ms, w->prof_ev[i + k], w->prof_ev[i + k + 1]));
+                    prof_ms[k] += ms;
+                }
+            prof_used = 0;
+        }
         k_deposit<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(b, d_accum, (int)npix, ns);
         s->stats.kernel_launches++;
         TRT_CUDA(cudaGetLastError());
@@ -727,6 +800,8 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
     float ms = 0;
     TRT_CUDA(cudaEventElapsedTime(&ms, w->ev0, w->ev1));
     s->stats.last_render_ms = ms;
+    s->stats.ms_trace = prof_ms[0], s->stats.ms_shade = prof_ms[1], s->stats.ms_shadow = prof_ms[2];
+    s->stats.ms_accumulate = prof_ms[3];
     return TRT_OK;
 }
 

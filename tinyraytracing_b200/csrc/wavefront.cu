@@ -661,10 +661,12 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
         setLastError("more than 32 lights");
         return TRT_ERR_LIMIT;
     }
-    // Paths in flight per batch.  Every depth iteration costs five launches whatever the queue length and path
-    // counts decay by 0.8 per depth, so large batches amortise the long tail (measured, veach-mis 64 spp: 330 spp/s
-    // at 4 Mi paths, 390 at 16 Mi, 409 at 64 Mi).  Default 32 Mi paths, bounded by a quarter of the free memory.
-    long long target = p.batch_paths > 0 ? p.batch_paths : (32ll << 20);
+    // Paths in flight per batch.  Every depth iteration costs five launches and at least one wave of rays (~0.2 ms on
+    // staircase) whatever the queue length, and path counts decay by 0.8 per depth, so large batches amortise the
+    // long tail.  Measured: veach-mis 1280x720 256 spp 506.7 / 499.6 / 493.6 ms and staircase 1920x1080 128 spp
+    // 2127 / 2102 / 2094 ms at 32 / 64 / 128 Mi paths.  Default 128 Mi paths (52 GB of path state with 6 lights:
+    // HBM is 180 GB and the scene itself is megabytes), bounded by a third of the free memory.
+    long long target = p.batch_paths > 0 ? p.batch_paths : (128ll << 20);
     if (p.batch_paths <= 0)
     {
         size_t free_b = 0, total_b = 0;
@@ -672,8 +674,10 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
         {
             const long long per_path = 100 + 48ll * std::max(1, s->view.n_lights);
             const long long have = (long long)(s->wf ? (size_t)s->wf->capacity * per_path : 0);
-            target = std::min(target, std::max(1ll << 20, ((long long)free_b / 4 + have) / per_path));
+            target = std::min(target, std::max(1ll << 20, ((long long)free_b / 3 + have) / per_path));
         }
+        // slot * n_lights + light must fit 32-bit indices (checked below for explicit batch sizes)
+        target = std::min(target, 0x7fffffffll / std::max(1, s->view.n_lights));
     }
     const int total_samples = p.sample_end - p.sample_begin;
     if (total_samples <= 0)

@@ -95,6 +95,7 @@ struct SceneView
     const TriGeom *fast_geom;
     const uint32_t *fast_key, *fast_rank;
     const int32_t *fast_orig, *fast_leaf;
+    const int32_t *fast_mtl; // material of each fast-layout triangle (the only thing a light-sample ray needs of its hit)
     const float4 *ref_leaf_box; // 2 per reference leaf: (AA.xyz, -) (BB.xyz, -)
     int32_t check_leaf_box;     // 0 only when the whole scene is ONE reference leaf (scanned without a box test)
     float strict_origin_limit;  // rays starting farther than this from the coordinate origin take the strict walk

@@ -225,6 +225,13 @@ int trt_scene_create(const trt_scene_desc *desc, int device, trt_scene **out)
     }
     if ((rc = upload(s.get(), shade.data(), shade.size(), &v.tri_shade)))
         return rc;
+    {
+        std::vector<int32_t> fast_mtl(ab.fast_orig.size());
+        for (size_t i = 0; i < fast_mtl.size(); ++i)
+            fast_mtl[i] = desc->mtl[ab.fast_orig[i]];
+        if ((rc = upload(s.get(), fast_mtl.data(), fast_mtl.size(), &v.fast_mtl)))
+            return rc;
+    }
 
     std::vector<DeviceTexture> tex(desc->n_textures);
     for (int i = 0; i < desc->n_textures; ++i)

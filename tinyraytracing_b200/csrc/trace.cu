@@ -47,13 +47,19 @@ struct BatchRays
     const float *rays6;
     int32_t *out_id;
     float *out_t;
-    __device__ __forceinline__ void load(size_t i, float3 &S, float3 &d) const { loadRay(rays6, i, S, d); }
-    __device__ __forceinline__ void store(size_t i, const Hit &h) const
+    __device__ __forceinline__ unsigned int locate(unsigned int i) const { return i; }
+    __device__ __forceinline__ void load(unsigned int i, float3 &S, float3 &d) const { loadRay(rays6, i, S, d); }
+    __device__ __forceinline__ void store(unsigned int i, const Hit &h) const
     {
         if (out_id)
             out_id[i] = h.id;
         if (out_t)
             out_t[i] = h.t;
+    }
+    __device__ __forceinline__ void storeFast(const SceneView &sv, unsigned int i, Hit h) const
+    {
+        h.id = (h.id >= 0) ? __ldg(sv.fast_orig + h.id) : -1; // fast index -> post-build index
+        store(i, h);
     }
 };
 

@@ -460,7 +460,9 @@ __device__ __forceinline__ void walkPoolInside(const SceneView &sv, const WalkSt
     }
 }
 
-// RAYS: struct with  __device__ bool load(size_t i, float3 &S, float3 &d)  and  void store(size_t i, const Hit &).
+// RAYS: struct with  unsigned locate(unsigned i)  (ray index -> the 32-bit token the walker keeps while the ray is in
+// flight, never 0xffffffff),  void load(token, float3 &S, float3 &d),  void store(token, const Hit &)  (hit.id = post-build
+// triangle index)  and  void storeFast(sv, token, const Hit &)  (hit.id = index in the fast layout's own order).
 // `counter` must be zero at launch; n = number of rays.  Every thread of the block must call this.
 // POOLED selects the leaf phase: false = every lane scans its own leaf (scanLeaf); true = the warp pools the
 // candidates that pass the plane test and deals their inside tests out one per lane (see below; measured in
@@ -506,8 +508,8 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                 const unsigned int mine = base + (unsigned int)__popc(idle & ((1u << lane) - 1u));
                 if (mine < n)
                 {
-                    ray = mine;
-                    rays.load(mine, st.S, st.d);
+                    ray = rays.locate(mine);
+                    rays.load(ray, st.S, st.d);
                     st.hit.t = TRT_INF, st.hit.id = -1, st.hit.key = 0xFFFFFFFFu;
                     if (!sv.use_wide || needsStrictWalk(sv, st.S, st.d))
                     {
@@ -634,10 +636,10 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                 const unsigned long long b = best[lane];
                 st.hit.t = __uint_as_float((unsigned int)(b >> 32));
                 st.hit.id = __ldg(sv.rank_tri + (unsigned int)b);
+                rays.store(ray, st.hit);
             }
             else
-                st.hit.id = (st.hit.id >= 0) ? __ldg(sv.fast_orig + st.hit.id) : -1;
-            rays.store(ray, st.hit);
+                rays.storeFast(sv, ray, st.hit);
             ray = 0xffffffffu;
         }
     }

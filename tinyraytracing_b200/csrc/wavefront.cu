@@ -156,52 +156,64 @@ __global__ void __launch_bounds__(kBlock) k_raygen(SceneView sv, WfBuffers wf, i
 }
 
 // ------------------------------------------------------------------------------------------------ K2 / K4
-struct QueueRays // closest-hit rays of the live paths
+struct QueueRays // closest-hit rays of the live paths; token = path slot
 {
     WfBuffers wf;
     int qsel;
-    __device__ __forceinline__ void load(size_t i, float3 &S, float3 &d) const
+    __device__ __forceinline__ unsigned int locate(unsigned int i) const { return (unsigned int)wf.queue[qsel][i]; }
+    __device__ __forceinline__ void load(unsigned int slot, float3 &S, float3 &d) const
     {
-        const int slot = wf.queue[qsel][i];
         S = xyz(wf.ray_o[slot]), d = xyz(wf.ray_d[slot]);
     }
-    __device__ __forceinline__ void store(size_t i, const Hit &h) const
+    __device__ __forceinline__ void store(unsigned int slot, const Hit &h) const
     {
-        const int slot = wf.queue[qsel][i];
         wf.hit_id[slot] = h.id;
         wf.hit_t[slot] = h.t;
     }
+    __device__ __forceinline__ void storeFast(const SceneView &sv, unsigned int slot, Hit h) const
+    {
+        h.id = (h.id >= 0) ? __ldg(sv.fast_orig + h.id) : -1; // fast index -> post-build index
+        store(slot, h);
+    }
 };
 
-struct ShadowRays // light-sample rays, one queue segment per light (neighbouring lanes: same light, nearby pixels)
+// light-sample rays, one queue segment per light (neighbouring lanes: same light, nearby pixels); token = entry index
+// in sh_o / sh_d (light * capacity + position, below 2^31 by the batch-size check of renderAccumulate)
+struct ShadowRays
 {
     WfBuffers wf;
     const TriShade *tri_shade;
     int n_lights;
-    __device__ __forceinline__ size_t locate(size_t i) const
+    __device__ __forceinline__ unsigned int locate(unsigned int i) const
     {
         int l = 0;
         for (; l < n_lights - 1; ++l)
         {
-            const size_t c = (size_t)wf.counters[kShadowCount + l];
+            const unsigned int c = (unsigned int)wf.counters[kShadowCount + l];
             if (i < c)
                 break;
             i -= c;
         }
-        return (size_t)l * wf.capacity + i;
+        return (unsigned int)l * (unsigned int)wf.capacity + i;
     }
-    __device__ __forceinline__ void load(size_t i, float3 &S, float3 &d) const
+    __device__ __forceinline__ void load(unsigned int e, float3 &S, float3 &d) const
     {
-        const size_t e = locate(i);
         S = xyz(wf.sh_o[e]), d = xyz(wf.sh_d[e]);
     }
-    __device__ __forceinline__ void store(size_t i, const Hit &h) const
+    // pathTracing.cpp:54-58: visible iff the closest hit's material is the light's material
+    __device__ __forceinline__ void finish(unsigned int e, bool hit, int mtl) const
     {
-        const size_t e = locate(i);
-        // pathTracing.cpp:54-58: visible iff the closest hit's material is the light's material
-        const bool visible = h.id >= 0 && tri_shade[h.id].mtl == __float_as_int(wf.sh_d[e].w);
+        const bool visible = hit && mtl == __float_as_int(wf.sh_d[e].w);
         if (!visible)
             wf.sh_contrib[__float_as_int(wf.sh_o[e].w)] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __device__ __forceinline__ void store(unsigned int e, const Hit &h) const
+    {
+        finish(e, h.id >= 0, h.id >= 0 ? tri_shade[h.id].mtl : -1);
+    }
+    __device__ __forceinline__ void storeFast(const SceneView &sv, unsigned int e, const Hit &h) const
+    {
+        finish(e, h.id >= 0, h.id >= 0 ? __ldg(sv.fast_mtl + h.id) : -1); // one load from a dense 4-byte table
     }
 };
 
@@ -211,14 +223,15 @@ __device__ __forceinline__ void traceGridStride(const SceneView &sv, RAYS &rays,
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     {
+        const unsigned int token = rays.locate((unsigned int)i);
         float3 S, d;
-        rays.load(i, S, d);
+        rays.load(token, S, d);
         Hit hit;
         if (MODE == 1)
             traceRefTopology<false>(sv, S, d, hit);
         else
             traceClosest(sv, S, d, hit);
-        rays.store(i, hit);
+        rays.store(token, hit);
     }
 }
 
@@ -233,8 +246,11 @@ __global__ void __launch_bounds__(kBlock) k_trace(SceneView sv, WfBuffers wf, in
         walkPersistent<false>(sv, r, n, reinterpret_cast<unsigned int *>(wf.counters + kPoolTrace));
 }
 
+// 9 resident CTAs per SM = 56 registers (24 bytes of spills) instead of 64 / 8 CTAs: the walker is latency-bound (ncu:
+// 1.4 eligible warps per cycle), one more CTA of warps pays (staircase 72.1 -> 70.8 ms of k_shadow, veach-mis 32.6 -> 32.2);
+// 10 CTAs = 48 registers spill 134 bytes and lose (83.6 ms).  k_trace needs 56 registers as it is.
 template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_shadow(SceneView sv, WfBuffers wf)
+__global__ void __launch_bounds__(kBlock, 9) k_shadow(SceneView sv, WfBuffers wf)
 {
     ShadowRays r{wf, sv.tri_shade, sv.n_lights};
     unsigned int n = 0;

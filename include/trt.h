@@ -190,6 +190,22 @@ typedef struct trt_stats {
     double ms_trace, ms_shade, ms_shadow, ms_accumulate;
 } trt_stats;
 
+/* ---- host-only: build the GPU layouts for `desc` and verify their invariants (no device needed) ------------------
+   What the exactness argument needs of the fast layout and a kernel cannot check: every triangle that
+   interactTriangle (bvh.cpp:177-209) could accept is in exactly one leaf, carries the reference leaf (bvh.cpp:43-48)
+   it belongs to, and lies — with the pad — inside every box on its path from the root; the tree fits the per-thread
+   stack.  violations == 0 on success; returns TRT_ERR_INVALID with the first violation in trt_last_error otherwise. */
+typedef struct trt_layout_report {
+    int32_t n_tris;        /* triangles of the scene                                                       */
+    int32_t n_fast_tris;   /* triangles in the fast layout                                                 */
+    int32_t n_dropped;     /* left out: NaN face normal / non-finite vertex (can never be hit)              */
+    int32_t use_wide;      /* 0: scene keeps the reference-topology kernels (single leaf / too deep / empty) */
+    int32_t wide_nodes, wide_depth, ref_leaves, ref_depth, slivers, needles;
+    int32_t violations;
+    double sah_wide;       /* expected child-box tests per random ray through the root box (surface-area heuristic) */
+} trt_layout_report;
+int trt_layout_check(const trt_scene_desc *desc, trt_layout_report *report);
+
 int trt_get_stats(trt_scene *scene, trt_stats *out);
 int trt_reset_stats(trt_scene *scene);
 const char *trt_last_error(void);

@@ -153,3 +153,63 @@ def test_png_writer_roundtrip(tmp_path):
     big = rng.integers(0, 256, (300, 300, 3), dtype=np.uint8)  # > 64 KiB: several stored deflate blocks
     assert trt.load_library().trt_write_png(p.encode(), 300, 300, big.ctypes.data, 0) == 0
     assert np.array_equal(cv2.imread(p, cv2.IMREAD_COLOR)[:, :, ::-1], big)
+
+
+# ---- fast-layout invariants, checked on the host (trt_layout_check) -----------------------------------------------
+def _random_soup(n_tris, seed, scale=1.0, degenerate=0):
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-1, 1, (n_tris, 1, 3)) * scale
+    v = (c + rng.normal(size=(n_tris, 3, 3)) * 0.05 * scale).astype(np.float32)
+    for k in range(min(degenerate, n_tris)):
+        v[k, 2] = v[k, 1]  # zero-area triangle: scene.cpp:196 gives it a NaN face normal
+    mats = [dict(Kd=(0.5, 0.5, 0.5), Ks=(0, 0, 0), Tr=(1, 1, 1), Ns=1.0, Ni=1.0)]
+    return trt.HostScene.from_arrays(v.reshape(-1, 9), np.zeros(n_tris, np.int32), mats, [], (0.0, 0.0, -4.0 * scale),
+                                     (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), 40.0, 16, 16)
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_fast_layout_invariants_on_the_cg22_scenes(name, host_scenes):
+    """Every triangle interactTriangle could accept is in exactly one leaf of the fast layout, tagged with its
+    reference leaf (bvh.cpp:43-48), inside every box on its path with the pad; the tree fits the traversal stack."""
+    rep = host_scenes[name].layout_check()
+    assert rep["violations"] == 0 and rep["use_wide"] == 1
+    assert rep["n_fast_tris"] + rep["n_dropped"] == rep["n_tris"]
+    # staircase: 2 432 zero-area triangles (NaN normal, SURVEY App. C) can never be hit and are left out
+    assert rep["n_dropped"] == {"back": 0, "veach-mis": 0, "staircase": 2432}[name]
+    assert 3 * rep["wide_depth"] + 2 <= 96
+
+
+@pytest.mark.parametrize("n_tris", (0, 1, 2, 3, 8, 9, 17, 1000))
+def test_fast_layout_invariants_on_small_and_degenerate_inputs(n_tris):
+    rep = _random_soup(n_tris, seed=n_tris, degenerate=n_tris // 5).layout_check()
+    assert rep["violations"] == 0
+    assert rep["n_tris"] == n_tris and rep["n_fast_tris"] + rep["n_dropped"] == n_tris or rep["use_wide"] == 0
+    if n_tris == 0:
+        assert rep["use_wide"] == 0 and rep["wide_nodes"] == 0
+
+
+@pytest.mark.parametrize("scale", (1e-3, 1.0, 1e3, 1e5))
+def test_fast_layout_pad_follows_the_scene_scale(scale):
+    """The pad is 256 ulp(scene scale): the checker recomputes it from the reference leaf boxes."""
+    rep = _random_soup(500, seed=7, scale=scale).layout_check()
+    assert rep["violations"] == 0 and rep["n_fast_tris"] == 500
+
+
+def test_fast_layout_invariants_on_the_stress_mesh():
+    from tinyraytracing_b200 import workloads
+
+    m = workloads.stress_mesh(71)
+    cam = m["camera"]
+    h = trt.HostScene.from_arrays(m["v9"], m["mtl"], m["materials"], m["lights"], cam["eye"], cam["lookat"], cam["up"],
+                                  cam["fovy"], 64, 36, vn9=m["vn9"])
+    rep = h.layout_check()
+    assert rep["violations"] == 0 and rep["n_fast_tris"] == rep["n_tris"] and rep["wide_nodes"] > 1000
+
+
+def test_leaf_atomic_layout_invariants(host_scenes, monkeypatch):
+    """TRT_WIDE_SOURCE=leaves (the first design, still selectable): reference leaves are the scan units."""
+    monkeypatch.setenv("TRT_WIDE_SOURCE", "leaves")
+    rep = host_scenes["veach-mis"].layout_check()
+    assert rep["violations"] == 0 and rep["n_fast_tris"] == rep["n_tris"]
+    monkeypatch.setenv("TRT_WIDE_SOURCE", "off")
+    assert host_scenes["veach-mis"].layout_check()["use_wide"] == 0

@@ -61,10 +61,16 @@ class Stats(C.Structure):
                 ("ms_accumulate", C.c_double)]
 
 
+class LayoutReport(C.Structure):
+    _fields_ = [("n_tris", C.c_int32), ("n_fast_tris", C.c_int32), ("n_dropped", C.c_int32), ("use_wide", C.c_int32),
+                ("wide_nodes", C.c_int32), ("wide_depth", C.c_int32), ("ref_leaves", C.c_int32), ("ref_depth", C.c_int32),
+                ("slivers", C.c_int32), ("needles", C.c_int32), ("violations", C.c_int32), ("sah_wide", C.c_double)]
+
+
 # every symbol include/trt.h and include/trt_host.h declare (tests check the library exports all of them)
 EXPORTS = ["trt_device_count", "trt_scene_create", "trt_scene_destroy", "trt_host_alloc", "trt_host_free",
            "trt_trace_closest", "trt_trace_closest_async", "trt_trace_counters", "trt_hit_attributes", "trt_render",
-           "trt_render_accumulate", "trt_resolve", "trt_get_stats", "trt_reset_stats", "trt_last_error",
+           "trt_render_accumulate", "trt_resolve", "trt_layout_check", "trt_get_stats", "trt_reset_stats", "trt_last_error",
            "trt_version", "trt_host_scene_load", "trt_host_scene_from_arrays", "trt_host_scene_desc",
            "trt_host_scene_faces", "trt_host_scene_material_name", "trt_host_scene_build_seconds",
            "trt_host_scene_free", "trt_decode_jpeg", "trt_write_png"]
@@ -101,6 +107,7 @@ def load_library():
     L.trt_hit_attributes.argtypes = [vp, vp, vp, vp, sz, vp, vp]
     L.trt_trace_counters.argtypes = [vp, vp, sz, vp]
     L.trt_render.argtypes = [vp, C.POINTER(RenderParams), vp]
+    L.trt_layout_check.argtypes = [C.POINTER(SceneDesc), C.POINTER(LayoutReport)]
     L.trt_render_accumulate.argtypes = [vp, C.POINTER(RenderParams), vp, vp]
     L.trt_resolve.argtypes = [vp, vp, i32, vp, vp, vp]
     L.trt_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -153,6 +160,12 @@ class HostScene:
         self.h = handle
         self.lib = load_library()
         self.desc = self.lib.trt_host_scene_desc(self.h).contents
+
+    def layout_check(self):
+        """Builds the GPU layouts on the host and verifies their invariants (trt_layout_check, no device needed)."""
+        rep = LayoutReport()
+        _check(self.lib.trt_layout_check(C.byref(self.desc), C.byref(rep)), "trt_layout_check")
+        return {k: getattr(rep, k) for k, _ in LayoutReport._fields_}
 
     @classmethod
     def load(cls, xml, obj, mtl, basedir, leaf_num=8):

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <future>
 #include <cstdlib>
+#include <cstring>
 #include <functional>
 
 namespace trt
@@ -512,5 +513,193 @@ std::string buildWide(const trt_scene_desc &desc, AccelBuild &out)
         return "wide layout too deep for its stack";
     }
     return "";
+}
+
+// ------------------------------------------------------------------------------------------------------------
+std::string checkLayout(const trt_scene_desc &desc, const AccelBuild &ab, trt_layout_report &rep)
+{
+    const int n = desc.n_tris, nn = desc.n_nodes;
+    rep = trt_layout_report();
+    rep.n_tris = n;
+    rep.n_fast_tris = (int32_t)ab.fast_orig.size();
+    rep.wide_nodes = (int32_t)ab.wide_nodes.size();
+    rep.wide_depth = ab.wide_depth;
+    rep.ref_leaves = ab.n_leaves;
+    rep.ref_depth = ab.ref_depth;
+    rep.slivers = ab.n_sliver, rep.needles = ab.n_needle;
+    rep.sah_wide = ab.sah_wide;
+    rep.use_wide = (ab.wide_root != TRT_LINK_EMPTY) ? 1 : 0;
+    std::string first;
+    auto bad = [&](const std::string &what) {
+        if (rep.violations++ == 0)
+            first = what;
+    };
+    const size_t nf = ab.fast_orig.size();
+    if (ab.fast_geom.size() != nf || ab.fast_key.size() != nf || ab.fast_leaf.size() != nf || ab.fast_rank.size() != nf)
+        bad("fast arrays differ in length");
+    if (rep.violations)
+        return first;
+
+    // reference leaf of every triangle, leaf boxes in node order
+    std::vector<int32_t> leafOfTri(n, -1);
+    std::vector<const float *> leafBox;
+    float scale = 0.f;
+    for (int i = 0; i < nn; ++i)
+    {
+        const int32_t *lk = desc.node_link + (size_t)i * 4;
+        if (lk[3] <= 0)
+            continue;
+        for (int k = 0; k < lk[3]; ++k)
+            leafOfTri[lk[2] + k] = (int32_t)leafBox.size();
+        leafBox.push_back(desc.node_box + (size_t)i * 6);
+        for (int a = 0; a < 6; ++a)
+            if (std::isfinite(leafBox.back()[a]))
+                scale = std::fmax(scale, std::fabs(leafBox.back()[a]));
+    }
+    if (!rep.use_wide)
+        return first; // the scene keeps the reference-topology kernels: there is no fast layout to check
+    if (ab.ref_leaf_box.size() != 2 * leafBox.size())
+        bad("ref_leaf_box does not hold one box per reference leaf");
+    else
+        for (size_t l = 0; l < leafBox.size(); ++l)
+        {
+            const float4 lo = ab.ref_leaf_box[2 * l], hi = ab.ref_leaf_box[2 * l + 1];
+            const float *b = leafBox[l];
+            if (std::memcmp(&lo, b, 12) != 0 || std::memcmp(&hi, b + 3, 12) != 0)
+                bad("ref_leaf_box differs from the reference's leaf box");
+        }
+
+    // every triangle at most once, the missing ones can never be hit, per-triangle data carried over bit for bit
+    std::vector<int32_t> seen(n, 0);
+    for (size_t i = 0; i < nf; ++i)
+    {
+        const int32_t t = ab.fast_orig[i];
+        if (t < 0 || t >= n)
+        {
+            bad("fast_orig out of range");
+            continue;
+        }
+        if (seen[t]++)
+            bad("triangle appears twice in the fast layout");
+        if (ab.fast_leaf[i] != leafOfTri[t])
+            bad("fast_leaf is not the triangle's reference leaf");
+        if (std::memcmp(&ab.fast_geom[i], &ab.tri_geom[t], sizeof(TriGeom)) != 0 || ab.fast_key[i] != ab.tri_key[t] ||
+            ab.fast_rank[i] != ab.tri_rank[t])
+            bad("fast_geom / fast_key / fast_rank differ from the post-build arrays");
+    }
+    if (rep.use_wide)
+        for (int t = 0; t < n; ++t)
+        {
+            if (seen[t])
+                continue;
+            ++rep.n_dropped;
+            const float *v = desc.v + (size_t)t * 9, *N = desc.normal + (size_t)t * 3;
+            bool finite = std::isfinite(N[0]) && std::isfinite(N[1]) && std::isfinite(N[2]);
+            for (int k = 0; k < 9; ++k)
+                finite = finite && std::isfinite(v[k]);
+            if (finite && leafOfTri[t] >= 0)
+                bad("a triangle that can be hit is missing from the fast layout");
+        }
+    if (!rep.use_wide || rep.violations)
+        return first;
+
+    // walk the tree: leaves tile [0, nf), every node is reached once, boxes nest and hold their triangles with the pad
+    const float pad = 256.f * (std::nextafter(scale, INFINITY) - scale);
+    std::vector<int32_t> covered(nf, 0), visited(ab.wide_nodes.size(), 0);
+    auto leafInside = [&](int32_t link, const float *lo, const float *hi) {
+        const int first = (~link) >> 3, count = ((~link) & 7) + 1;
+        if (first < 0 || (size_t)first + count > nf)
+        {
+            bad("leaf link out of range");
+            return;
+        }
+        for (int i = first; i < first + count; ++i)
+        {
+            covered[i]++;
+            const float *v = desc.v + (size_t)ab.fast_orig[i] * 9;
+            const float *rb = leafBox[ab.fast_leaf[i]];
+            bool padded = true, plain = true, refbox = true;
+            for (int a = 0; a < 3; ++a)
+            {
+                const float vlo = std::fmin(v[a], std::fmin(v[3 + a], v[6 + a])), vhi = std::fmax(v[a], std::fmax(v[3 + a], v[6 + a]));
+                padded = padded && lo[a] <= vlo - pad && hi[a] >= vhi + pad;
+                plain = plain && lo[a] <= vlo && hi[a] >= vhi;
+                refbox = refbox && lo[a] <= rb[a] && hi[a] >= rb[3 + a];
+            }
+            // a needle keeps its reference leaf's box (which holds its vertices); everything else gets the pad
+            if (!plain || !(padded || refbox))
+                bad("a box on the path to a triangle does not contain it with the pad");
+        }
+    };
+    if (ab.wide_root < 0)
+    {
+        const float lo[3] = {-INFINITY, -INFINITY, -INFINITY}, hi[3] = {INFINITY, INFINITY, INFINITY};
+        leafInside(ab.wide_root, lo, hi); // single scan unit: no box of this layout is tested
+    }
+    else
+    {
+        struct Item
+        {
+            int32_t node, depth;
+            float lo[3], hi[3];
+        };
+        std::vector<Item> todo;
+        todo.push_back({0, 1, {-INFINITY, -INFINITY, -INFINITY}, {INFINITY, INFINITY, INFINITY}});
+        int maxDepth = 0;
+        while (!todo.empty())
+        {
+            const Item it = todo.back();
+            todo.pop_back();
+            if (it.node < 0 || (size_t)it.node >= ab.wide_nodes.size())
+            {
+                bad("inner link out of range");
+                continue;
+            }
+            if (visited[it.node]++)
+            {
+                bad("wide node reached twice");
+                continue;
+            }
+            maxDepth = it.depth > maxDepth ? it.depth : maxDepth;
+            const WideNode &w = ab.wide_nodes[it.node];
+            const float *lox = &w.lox.x, *loy = &w.loy.x, *loz = &w.loz.x, *hix = &w.hix.x, *hiy = &w.hiy.x, *hiz = &w.hiz.x;
+            const int32_t *lk = &w.link.x;
+            int nk = 0;
+            for (int k = 0; k < 4; ++k)
+            {
+                if (lk[k] == TRT_LINK_EMPTY)
+                {
+                    if (k < 2)
+                        bad("a wide node needs at least two children in slots 0 and 1");
+                    continue;
+                }
+                ++nk;
+                const float lo[3] = {lox[k], loy[k], loz[k]}, hi[3] = {hix[k], hiy[k], hiz[k]};
+                for (int a = 0; a < 3; ++a)
+                    if (!(lo[a] <= hi[a]) || !(lo[a] >= it.lo[a]) || !(hi[a] <= it.hi[a]))
+                        bad("child box not finite, inverted, or not inside its parent's box");
+                if (lk[k] < 0)
+                    leafInside(lk[k], lo, hi);
+                else
+                {
+                    Item c{lk[k], it.depth + 1, {lo[0], lo[1], lo[2]}, {hi[0], hi[1], hi[2]}};
+                    todo.push_back(c);
+                }
+            }
+            if (nk < 2)
+                bad("wide node with fewer than two children");
+        }
+        for (size_t i = 0; i < visited.size(); ++i)
+            if (!visited[i])
+                bad("unreachable wide node");
+        if (maxDepth != ab.wide_depth)
+            bad("wide_depth differs from the tree's depth");
+        if (3 * maxDepth + 2 > TRT_WIDE_STACK)
+            bad("tree deeper than the traversal stack allows");
+    }
+    for (size_t i = 0; i < nf; ++i)
+        if (covered[i] != 1)
+            bad("a fast-layout triangle is not in exactly one leaf");
+    return first;
 }
 } // namespace trt

@@ -143,6 +143,9 @@ struct AccelBuild
 
 // Builds the layouts from the reference topology in `desc`. Returns "" or an error text.
 std::string buildAccel(const trt_scene_desc &desc, AccelBuild &out);
+// Host-side verification of the fast layout's structural invariants (the ones the exactness argument of DESIGN.md §3
+// rests on); fills `report`, returns "" or the first violation.
+std::string checkLayout(const trt_scene_desc &desc, const AccelBuild &ab, trt_layout_report &report);
 // Builds the 4-wide fast layout over the reference leaves into `out` (after buildAccel). A non-empty return
 // means the layout is unavailable for this scene (the reference-topology kernels are used instead).
 std::string buildWide(const trt_scene_desc &desc, AccelBuild &out);

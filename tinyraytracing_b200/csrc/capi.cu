@@ -517,6 +517,21 @@ int trt_render(trt_scene *s, const trt_render_params *p, double *image_rgb)
     return rc;
 }
 
+int trt_layout_check(const trt_scene_desc *desc, trt_layout_report *report)
+{
+    if (!desc || !report)
+        return fail(TRT_ERR_INVALID, "trt_layout_check: null argument");
+    AccelBuild ab;
+    std::string err = buildAccel(*desc, ab);
+    if (!err.empty())
+        return fail(TRT_ERR_INVALID, "trt_layout_check: " + err);
+    buildWide(*desc, ab); // an error text here only means "this scene keeps the reference-topology kernels"
+    err = checkLayout(*desc, ab, *report);
+    if (!err.empty())
+        return fail(TRT_ERR_INVALID, "trt_layout_check: " + err);
+    return TRT_OK;
+}
+
 int trt_get_stats(trt_scene *s, trt_stats *out)
 {
     if (!s || !out)

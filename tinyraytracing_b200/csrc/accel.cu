@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <queue>
 
 namespace trt
 {
@@ -275,6 +276,208 @@ struct WideBuilder
         return me;
     }
 };
+
+// Insertion-based optimisation of the binary tree (after Bittner, Hapala, Havran: "Fast insertion-based optimization
+// of bounding volume hierarchies", 2013): an inner node whose box is large for what it holds is taken out, and its two
+// subtrees are re-inserted where they increase the summed surface area of the inner nodes least (branch-and-bound search
+// from the root).  Leaves — the sets of triangles — are never changed and every box stays the exact union of the padded
+// triangle boxes below it, so the layout's invariants (checkLayout) hold by construction; only the expected number of
+// box tests per ray (the SAH sum) drops.  Deterministic: no randomness, fixed visiting order.
+struct Reinserter
+{
+    std::vector<BNode> &bn;
+    int32_t n_nodes;
+    std::vector<int32_t> parent;
+    size_t max_per_pass = 200000;
+    std::vector<std::pair<float, int32_t>> heap_; // findTarget's queue, kept to avoid an allocation per search
+
+    explicit Reinserter(std::vector<BNode> &b, int32_t n) : bn(b), n_nodes(n), parent(n, -1)
+    {
+        for (int32_t i = 0; i < n; ++i)
+            if (bn[i].right != -2)
+                parent[bn[i].left] = i, parent[bn[i].right] = i;
+    }
+    bool isLeaf(int32_t i) const { return bn[i].right == -2; }
+    float area(int32_t i) const { return halfArea(bn[i].lo, bn[i].hi); }
+    float unionArea(int32_t a, int32_t b) const
+    {
+        float lo[3], hi[3];
+        for (int k = 0; k < 3; ++k)
+            lo[k] = std::fmin(bn[a].lo[k], bn[b].lo[k]), hi[k] = std::fmax(bn[a].hi[k], bn[b].hi[k]);
+        return halfArea(lo, hi);
+    }
+    // `start` is recomputed unconditionally (a re-used free node carries a stale box); above it the walk stops at the
+    // first node whose box does not change: every ancestor was the exact union of its children before
+    void refitUp(const int32_t start)
+    {
+        for (int32_t i = start; i >= 0; i = parent[i])
+        {
+            const BNode &l = bn[bn[i].left], &r = bn[bn[i].right];
+            bool changed = false;
+            for (int k = 0; k < 3; ++k)
+            {
+                const float lo = std::fmin(l.lo[k], r.lo[k]), hi = std::fmax(l.hi[k], r.hi[k]);
+                changed = changed || lo != bn[i].lo[k] || hi != bn[i].hi[k];
+                bn[i].lo[k] = lo, bn[i].hi[k] = hi;
+            }
+            if (!changed && i != start)
+                break;
+        }
+    }
+    double innerAreaSum() const
+    {
+        double sum = 0;
+        std::vector<int32_t> st{0};
+        while (!st.empty())
+        {
+            const int32_t i = st.back();
+            st.pop_back();
+            if (isLeaf(i))
+                continue;
+            sum += area(i);
+            st.push_back(bn[i].left), st.push_back(bn[i].right);
+        }
+        return sum;
+    }
+    int depth() const
+    {
+        int best = 0;
+        std::vector<std::pair<int32_t, int>> st{{0, 1}};
+        while (!st.empty())
+        {
+            const auto it = st.back();
+            st.pop_back();
+            best = std::max(best, it.second);
+            if (!isLeaf(it.first))
+                st.push_back({bn[it.first].left, it.second + 1}), st.push_back({bn[it.first].right, it.second + 1});
+        }
+        return best;
+    }
+    // best place for subtree x: the node t that x should become the sibling of (never the root)
+    int32_t findTarget(int32_t x)
+    {
+        const float ax = area(x);
+        float best = INFINITY;
+        int32_t target = -1;
+        typedef std::pair<float, int32_t> QE; // (induced cost of the ancestors, node), smallest first
+        std::vector<QE> &heap = heap_;
+        heap.clear();
+        auto push = [&](QE e) {
+            heap.push_back(e);
+            std::push_heap(heap.begin(), heap.end(), std::greater<QE>());
+        };
+        const float rootInduced = unionArea(0, x) - area(0);
+        push({rootInduced, bn[0].left}), push({rootInduced, bn[0].right});
+        while (!heap.empty())
+        {
+            std::pop_heap(heap.begin(), heap.end(), std::greater<QE>());
+            const QE e = heap.back();
+            heap.pop_back();
+            if (e.first + ax >= best)
+                break; // every remaining candidate costs at least its induced part plus area(x)
+            const float direct = unionArea(e.second, x);
+            if (e.first + direct < best)
+                best = e.first + direct, target = e.second;
+            const float below = e.first + direct - area(e.second);
+            if (!isLeaf(e.second) && below + ax < best)
+                push({below, bn[e.second].left}), push({below, bn[e.second].right});
+        }
+        return target;
+    }
+    void replaceChild(int32_t p, int32_t from, int32_t to)
+    {
+        (bn[p].left == from ? bn[p].left : bn[p].right) = to;
+        parent[to] = p;
+    }
+    // one pass over the inner nodes in decreasing order of the paper's combined inefficiency measure
+    void pass(double fraction)
+    {
+        std::vector<std::pair<float, int32_t>> cand;
+        for (int32_t i = 1; i < n_nodes; ++i)
+        {
+            if (isLeaf(i) || parent[i] <= 0) // needs a parent and a grandparent
+                continue;
+            const float a = area(i), al = area(bn[i].left), ar = area(bn[i].right);
+            const float msum = a / (0.5f * (al + ar) + 1e-30f), mmin = a / (std::fmin(al, ar) + 1e-30f);
+            cand.push_back({a * msum * mmin, i});
+        }
+        std::sort(cand.begin(), cand.end(), [](const std::pair<float, int32_t> &x, const std::pair<float, int32_t> &y) {
+            return x.first > y.first || (x.first == y.first && x.second < y.second);
+        });
+        // large scenes: the nodes that matter are the big ones near the top; a cap keeps the build time bounded
+        const size_t take = std::min((size_t)(fraction * (double)cand.size()), (size_t)max_per_pass);
+        for (size_t c = 0; c < take; ++c)
+        {
+            const int32_t n = cand[c].second;
+            if (isLeaf(n) || parent[n] <= 0)
+                continue; // restructured earlier in this pass
+            const int32_t p = parent[n], g = parent[p];
+            const int32_t sib = (bn[p].left == n) ? bn[p].right : bn[p].left;
+            int32_t sub[2] = {bn[n].left, bn[n].right};
+            if (area(sub[0]) < area(sub[1]))
+                std::swap(sub[0], sub[1]);
+            replaceChild(g, p, sib); // p and n are now free nodes
+            refitUp(g);
+            const int32_t freeNode[2] = {n, p};
+            for (int k = 0; k < 2; ++k)
+            {
+                const int32_t x = sub[k], t = findTarget(x), q = freeNode[k];
+                const int32_t pt = parent[t];
+                replaceChild(pt, t, q);
+                bn[q].left = t, bn[q].right = x;
+                parent[t] = q, parent[x] = q;
+                refitUp(q);
+            }
+        }
+    }
+};
+
+// Summed surface area of all child boxes of the 4-wide tree that the greedy collapse of buildWide makes of `bn` (the
+// expected number of box tests per random ray, up to the root's area), and that tree's depth.
+double collapseCost(const std::vector<BNode> &bn, int *depth_out)
+{
+    if (bn[0].right == -2)
+    {
+        *depth_out = 0;
+        return 0;
+    }
+    double sum = 0;
+    int maxDepth = 1;
+    std::vector<std::pair<int32_t, int>> todo{{0, 1}};
+    while (!todo.empty())
+    {
+        const auto it = todo.back();
+        todo.pop_back();
+        maxDepth = std::max(maxDepth, it.second);
+        int32_t kids[4] = {bn[it.first].left, bn[it.first].right, -1, -1};
+        int nk = 2;
+        while (nk < 4)
+        {
+            int pick = -1;
+            float best = -1.f;
+            for (int k = 0; k < nk; ++k)
+                if (bn[kids[k]].right != -2)
+                {
+                    const float a = halfArea(bn[kids[k]].lo, bn[kids[k]].hi);
+                    if (a > best)
+                        best = a, pick = k;
+                }
+            if (pick < 0)
+                break;
+            const int32_t c = kids[pick];
+            kids[pick] = bn[c].left;
+            kids[nk++] = bn[c].right;
+        }
+        for (int k = 0; k < nk; ++k)
+        {
+            sum += halfArea(bn[kids[k]].lo, bn[kids[k]].hi);
+            if (bn[kids[k]].right != -2)
+                todo.push_back({kids[k], it.second + 1});
+        }
+    }
+    *depth_out = maxDepth;
+    return sum;
+}
 } // namespace
 
 std::string buildWide(const trt_scene_desc &desc, AccelBuild &out)
@@ -403,6 +606,32 @@ std::string buildWide(const trt_scene_desc &desc, AccelBuild &out)
         wb.order[i] = (int32_t)i;
     wb.bn.resize(prims.size() * 2);
     wb.build(0, (int)prims.size());
+    {
+        // insertion-based optimisation (Reinserter above): up to two passes (one beyond 500 k triangles, where a pass
+        // costs seconds), keeping whichever tree — the binned-SAH one included — collapses to the cheapest 4-wide tree
+        // that still fits the traversal stack.  TRT_REINSERT=0 switches it off, =N sets the number of passes.
+        const char *renv = getenv("TRT_REINSERT");
+        const int maxPasses = renv ? atoi(renv) : (prims.size() > 500000 ? 1 : 2);
+        const int32_t used = wb.next.load();
+        if (maxPasses > 0 && used >= 7)
+        {
+            int depth = 0;
+            double bestCost = collapseCost(wb.bn, &depth);
+            std::vector<BNode> best(wb.bn.begin(), wb.bn.begin() + used);
+            Reinserter ri(wb.bn, used);
+            for (int pass = 0; pass < maxPasses; ++pass)
+            {
+                ri.pass(pass == 0 ? 1.0 : 0.5);
+                const double cost = collapseCost(wb.bn, &depth);
+                if (cost < bestCost && 3 * depth + 2 <= TRT_WIDE_STACK)
+                {
+                    bestCost = cost;
+                    std::copy(wb.bn.begin(), wb.bn.begin() + used, best.begin());
+                }
+            }
+            std::copy(best.begin(), best.end(), wb.bn.begin());
+        }
+    }
     const std::vector<BNode> &bn = wb.bn;
 
     // triangles of a binary leaf, appended to the fast arrays in leaf order; returns the leaf link

@@ -213,3 +213,17 @@ def test_leaf_atomic_layout_invariants(host_scenes, monkeypatch):
     assert rep["violations"] == 0 and rep["n_fast_tris"] == rep["n_tris"]
     monkeypatch.setenv("TRT_WIDE_SOURCE", "off")
     assert host_scenes["veach-mis"].layout_check()["use_wide"] == 0
+
+
+def test_tree_optimisation_is_deterministic_and_never_worse(host_scenes, monkeypatch):
+    """The insertion-based optimisation of the fast layout's tree keeps the binned-SAH tree when that collapses
+    cheaper, has no randomness, and leaves the invariants intact (TRT_REINSERT=0 switches it off)."""
+    for name in SCENES:
+        monkeypatch.delenv("TRT_REINSERT", raising=False)
+        a, b = host_scenes[name].layout_check(), host_scenes[name].layout_check()
+        assert a == b and a["violations"] == 0
+        monkeypatch.setenv("TRT_REINSERT", "0")
+        off = host_scenes[name].layout_check()
+        assert off["violations"] == 0 and off["n_fast_tris"] == a["n_fast_tris"]
+        assert a["sah_wide"] <= off["sah_wide"] * (1 + 1e-12)
+    monkeypatch.delenv("TRT_REINSERT", raising=False)

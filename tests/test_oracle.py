@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import oraclelib
-from conftest import SCENES
+from conftest import SCENES, SMALL_RES
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -108,3 +108,82 @@ def test_oracle_render_agrees_with_reference_statistically(name, oracle_scenes):
     floor = np.sqrt(((c1 - c2) ** 2).mean())
     assert np.sqrt(((co - c1) ** 2).mean()) <= 1.25 * floor
     assert np.sqrt(((co - c2) ** 2).mean()) <= 1.25 * floor
+
+
+# ---- the closed-form barycentric solve of csrc/barycentric.cuh, restated in numpy ---------------------------------
+def closed_form_bary(V, P):
+    """Least-squares solution of [v0 v1 v2; 1 1 1] b = [P; 1] (triangle.cpp:12-29) without a factorisation: in-plane
+    2x2 Gram solve for q = P - v0 and for v0, plus the sum-to-one slack u along the normal (derivation in the header
+    of tinyraytracing_b200/csrc/barycentric.cuh, which computes exactly this)."""
+    v0 = V[:, 0].astype(np.float64)
+    e1, e2, q = V[:, 1].astype(np.float64) - v0, V[:, 2].astype(np.float64) - v0, P.astype(np.float64) - v0
+    dot = lambda a, b: (a * b).sum(1)  # noqa: E731
+    g11, g12, g22 = dot(e1, e1), dot(e1, e2), dot(e2, e2)
+    inv = 1.0 / (g11 * g22 - g12 * g12)
+    a1, a2, c1, c2 = dot(e1, q), dot(e2, q), dot(e1, v0), dot(e2, v0)
+    p1, p2 = (a1 * g22 - a2 * g12) * inv, (a2 * g11 - a1 * g12) * inv
+    w1, w2 = (c1 * g22 - c2 * g12) * inv, (c2 * g11 - c1 * g12) * inv
+    n = np.cross(e1, e2)
+    vn, qn, nn = dot(v0, n), dot(q, n), dot(n, n)
+    u = vn * qn / (vn * vn + nn)
+    b1, b2 = p1 - u * w1, p2 - u * w2
+    return np.stack([1.0 + u - b1 - b2, b1, b2], 1)
+
+
+def exact_bary(Vi, Pi):
+    """The same least-squares problem by Cramer's rule on the normal equations in exact rational arithmetic."""
+    from fractions import Fraction as Fr
+
+    A = [[Fr(float(Vi[j][i])) for j in range(3)] for i in range(3)] + [[Fr(1)] * 3]
+    c = [Fr(float(x)) for x in Pi] + [Fr(1)]
+    G = [[sum(A[k][i] * A[k][j] for k in range(4)) for j in range(3)] for i in range(3)]
+    h = [sum(A[k][i] * c[k] for k in range(4)) for i in range(3)]
+
+    def det3(M):
+        return (M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0])
+                + M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]))
+
+    D, out = det3(G), []
+    for i in range(3):
+        M = [row[:] for row in G]
+        for r in range(3):
+            M[r][i] = h[r]
+        out.append(float(det3(M) / D))
+    return out
+
+
+def test_closed_form_barycentrics_against_exact_arithmetic():
+    """0.01-sized triangles 1000 units from the origin, hit points rounded to float (so they sit off the plane, which
+    is what makes the sum-to-one row matter): the closed form agrees with exact arithmetic to 1e-13, where a double
+    SVD / QR solve of the 4x3 system is only good to ~1e-9 there."""
+    rng = np.random.default_rng(0)
+    n = 200
+    c = rng.uniform(-1, 1, (n, 1, 3)) * 1000
+    V = (c + rng.normal(size=(n, 3, 3)) * 0.01).astype(np.float32)
+    b = rng.dirichlet((1, 1, 1), n)
+    P = (V * b[:, :, None]).sum(1).astype(np.float32)
+    ex = np.array([exact_bary(V[i], P[i]) for i in range(n)])
+    assert np.abs(closed_form_bary(V, P) - ex).max() <= 1e-13
+    lst = np.array([np.linalg.lstsq(np.vstack([V[i].T.astype(np.float64), np.ones(3)]),
+                                    np.concatenate([P[i].astype(np.float64), [1.0]]), rcond=None)[0] for i in range(n)])
+    assert np.abs(lst - ex).max() > 1e-12  # the factorisation route is the less accurate one
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_closed_form_barycentrics_give_the_reference_pn(name, oracle_scenes):
+    """pn = normalize(sum vn_k b_k) (bvh.cpp:223-224) from the closed form equals the pn the unmodified reference
+    computed through Eigen's QR (golden fixture), to the 1e-6 the GPU tests use."""
+    g = np.load(os.path.join(GOLD, name + "_closest.npz"))
+    o = oracle_scenes[name]
+    ids, t, pn, hp = o.trace(g["rays"], want_pn=True)
+    hit = ids >= 0
+    ps = oraclelib.parsed_scene(name, *SMALL_RES[name])
+    order = o.order()
+    V = ps["v"].reshape(-1, 3, 3)[order][ids[hit]]
+    VN = ps["vn"].reshape(-1, 3, 3)[order][ids[hit]]
+    b = closed_form_bary(V, hp[hit]).astype(np.float32)
+    m = (VN[:, 0] * b[:, :1] + VN[:, 1] * b[:, 1:2]) + VN[:, 2] * b[:, 2:3]
+    mine = m / np.sqrt((m * m).sum(1, keepdims=True))
+    ok = np.isfinite(g["pn"][hit]).all(axis=1) & np.isfinite(mine).all(axis=1)
+    assert ok.sum() > 1000
+    assert np.abs(mine[ok] - g["pn"][hit][ok]).max() <= 1e-6

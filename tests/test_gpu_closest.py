@@ -269,3 +269,40 @@ def test_scene_scale_and_far_origins(scale):
         assert len(bad) == 0, (name, scale, len(bad), rays[bad[0]], ids[bad[0]], oid[bad[0]])
         assert np.array_equal(t.view(np.uint32), ot.view(np.uint32)), (name, scale)
     dev.close()
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_zero_direction_components_with_origins_on_box_planes(name, host_scenes, oracle_scenes, device_scenes):
+    """Rays with one or two zero / denormal direction components (1/d overflows: the centre column of an axis-aligned
+    camera) walk the fast layout with the reference's whole root-to-leaf box path as the acceptance gate.  The hard
+    case is an origin coordinate EXACTLY on a reference box plane: (b - S) * inf = NaN inside interactAABB
+    (bvh.cpp:231-245), whose glm min / max semantics decide whether the reference descends.  Every traversal mode must
+    reproduce the oracle bit for bit."""
+    dev, orc, host = device_scenes[name], oracle_scenes[name], host_scenes[name]
+    boxes, links = host.nodes()
+    lo, hi = host.root_box()
+    rng = np.random.default_rng(17)
+    n = 40000
+    o = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    axis = rng.integers(0, 3, n)
+    d[np.arange(n), axis] = rng.choice(np.array([0.0, -0.0, 1e-42, -1e-42], np.float32), n)  # zero and denormal
+    two = rng.random(n) < 0.25
+    axis2 = (axis + 1 + rng.integers(0, 2, n)) % 3
+    d[two, axis2[two]] = 0.0
+    nz = np.abs(d).max(axis=1) > 0
+    d[nz] /= np.linalg.norm(d[nz].astype(np.float64), axis=1, keepdims=True).astype(np.float32)
+    d[np.arange(n), axis] = np.where(np.abs(d[np.arange(n), axis]) < 1e-30, d[np.arange(n), axis], 0.0)
+    # half of the origins: the zeroed axis' coordinate is a plane of a reference node box, bit for bit
+    pick = rng.integers(0, len(boxes), n)
+    side = rng.integers(0, 2, n)
+    plane = boxes[pick, axis + 3 * side]
+    on_plane = (rng.random(n) < 0.5) & np.isfinite(plane)
+    o[on_plane, axis[on_plane]] = plane[on_plane]
+    rays = np.concatenate([o, d], 1).astype(np.float32)
+    oid, ot = orc.trace(rays)
+    assert (oid >= 0).sum() > n // 20
+    for mode, flags in MODES.items():
+        ids, t = dev.trace_closest(rays, flags)
+        assert np.array_equal(ids, oid), (mode, int((ids != oid).sum()))
+        assert np.array_equal(t.view(np.uint32), ot.view(np.uint32)), mode

@@ -112,9 +112,26 @@ std::string buildAccel(const trt_scene_desc &desc, AccelBuild &out)
         o.a = make_float4(L[0], L[1], L[2], L[3]);
         o.b = make_float4(L[4], L[5], R[0], R[1]);
         o.c = make_float4(R[2], R[3], R[4], R[5]);
-        o.d = make_int4(link(lk[0]), link(lk[1]), 0, 0);
+        o.d = make_int4(link(lk[0]), link(lk[1]), -1, 0);
     }
     out.root_link = link(0);
+    // parent links (the path of boxes the reference tests on its way to a leaf, walked upwards by refPathPasses)
+    out.ref_leaf_parent.assign(n_leaves, -1);
+    for (int i = 0; i < nn; ++i)
+    {
+        if (inner_index[i] < 0)
+            continue;
+        const int32_t *lk = desc.node_link + (size_t)i * 4;
+        for (int side = 0; side < 2; ++side)
+        {
+            const int c = lk[side];
+            const int32_t token = (inner_index[i] << 1) | side;
+            if (inner_index[c] >= 0)
+                out.ref_nodes[inner_index[c]].d.z = token;
+            else
+                out.ref_leaf_parent[leaf_ord[c]] = token;
+        }
+    }
 
     // depth of the reference tree (iterative: staircase reaches 59, degenerate inputs may go deeper)
     std::vector<int> depth(nn, 0);

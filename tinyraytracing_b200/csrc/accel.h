@@ -18,7 +18,8 @@ namespace trt
 
 // ---- reference topology, two child boxes per inner node (64 B) --------------------------------------------
 // a = (L.AA.x L.AA.y L.AA.z L.BB.x)  b = (L.BB.y L.BB.z R.AA.x R.AA.y)  c = (R.AA.z R.BB.x R.BB.y R.BB.z)
-// d = (left link, right link, -, -);  link >= 0: inner node index;  link < 0: leaf, ~link = first<<3 | (num-1)
+// d = (left link, right link, parent, -);  link >= 0: inner node index;  link < 0: leaf, ~link = first<<3 | (num-1);
+// parent = (parent's inner index << 1) | (1 if this node is its right child), -1 for the root
 struct __align__(16) RefNode
 {
     float4 a, b, c;
@@ -97,6 +98,7 @@ struct SceneView
     const int32_t *fast_orig, *fast_leaf;
     const int32_t *fast_mtl; // material of each fast-layout triangle (the only thing a light-sample ray needs of its hit)
     const float4 *ref_leaf_box; // 2 per reference leaf: (AA.xyz, -) (BB.xyz, -)
+    const int32_t *ref_leaf_parent; // per reference leaf: (parent's inner index << 1) | right-child bit, -1 if the leaf is the root
     int32_t check_leaf_box;     // 0 only when the whole scene is ONE reference leaf (scanned without a box test)
     float strict_origin_limit;  // rays starting farther than this from the coordinate origin take the strict walk
     int32_t n_tris;
@@ -133,6 +135,7 @@ struct AccelBuild
     std::vector<uint32_t> fast_key, fast_rank;
     std::vector<int32_t> fast_orig, fast_leaf;
     std::vector<float4> ref_leaf_box;
+    std::vector<int32_t> ref_leaf_parent;
     bool root_is_reference_leaf = false;
     float scene_scale = 0.f;
     int32_t n_sliver = 0; // triangles whose box got the larger sliver pad

@@ -205,7 +205,8 @@ int trt_scene_create(const trt_scene_desc *desc, int device, trt_scene **out)
         (rc = upload(s.get(), ab.fast_rank.data(), ab.fast_rank.size(), &v.fast_rank)) ||
         (rc = upload(s.get(), ab.fast_orig.data(), ab.fast_orig.size(), &v.fast_orig)) ||
         (rc = upload(s.get(), ab.fast_leaf.data(), ab.fast_leaf.size(), &v.fast_leaf)) ||
-        (rc = upload(s.get(), ab.ref_leaf_box.data(), ab.ref_leaf_box.size(), &v.ref_leaf_box)))
+        (rc = upload(s.get(), ab.ref_leaf_box.data(), ab.ref_leaf_box.size(), &v.ref_leaf_box)) ||
+        (rc = upload(s.get(), ab.ref_leaf_parent.data(), ab.ref_leaf_parent.size(), &v.ref_leaf_parent)))
         return rc;
     v.check_leaf_box = ab.root_is_reference_leaf ? 0 : 1;
     v.strict_origin_limit = 4.0f * ab.scene_scale;

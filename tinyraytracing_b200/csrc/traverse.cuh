@@ -116,8 +116,31 @@ __device__ __forceinline__ bool childPass(float3 S, float3 inv, float ax, float 
 // FAST = true: the fast layout's own leaf order; a candidate counts only if the REFERENCE leaf that holds the
 // triangle passes the reference's slab test for this ray (the reference never tests a triangle otherwise), and
 // hit.id is the fast index until the walk ends (toPostBuildId).
+// The boxes the reference tests on its way from the root to reference leaf `leaf` (interactAABB on every node of the
+// path, bvh.cpp:156-166), with the reference's own arithmetic including its NaN behaviour: the leaf is scanned by the
+// reference iff all of them pass.  Used instead of the leaf-box-only gate for rays with a direction component whose
+// reciprocal overflows, where "leaf box passes" no longer implies "its ancestors pass".
+// (out of line and with plain pointer arguments: the rare path must not weigh on the register allocation of the walks)
+static __device__ __noinline__ bool refPathPasses(const int32_t *ref_leaf_parent, const RefNode *ref_nodes, int leaf, float3 S,
+                                                  float3 inv)
+{
+    int32_t p = __ldg(ref_leaf_parent + leaf);
+    while (p >= 0)
+    {
+        const float4 *np = reinterpret_cast<const float4 *>(ref_nodes + (p >> 1));
+        const float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
+        float t0;
+        const bool ok = (p & 1) ? boxPass(S, inv, b.z, b.w, c.x, c.y, c.z, c.w, t0) : boxPass(S, inv, a.x, a.y, a.z, a.w, b.x, b.y, t0);
+        if (!ok)
+            return false;
+        p = __ldg(reinterpret_cast<const int32_t *>(np + 3) + 2);
+    }
+    return true;
+}
+
 template <bool FAST>
-__device__ __forceinline__ void scanLeaf(const SceneView &sv, int first, int num, float3 S, float3 d, float3 inv, Hit &hit)
+__device__ __forceinline__ void scanLeaf(const SceneView &sv, int first, int num, float3 S, float3 d, float3 inv, Hit &hit,
+                                         bool pathGate = false)
 {
     const TriGeom *geom = FAST ? sv.fast_geom : sv.tri_geom;
     const uint32_t *keys = FAST ? sv.fast_key : sv.tri_key;
@@ -130,7 +153,12 @@ __device__ __forceinline__ void scanLeaf(const SceneView &sv, int first, int num
         float t;
         if (triangleHit(g, S, d, hit.t, t))
         {
-            if (FAST && sv.check_leaf_box)
+            if (FAST && pathGate)
+            {
+                if (!refPathPasses(sv.ref_leaf_parent, sv.ref_nodes, __ldg(sv.fast_leaf + i), S, inv))
+                    continue;
+            }
+            else if (FAST && sv.check_leaf_box)
             {
                 const float4 *bp = sv.ref_leaf_box + 2 * __ldg(sv.fast_leaf + i);
                 const float4 lo = __ldg(bp), hi = __ldg(bp + 1);
@@ -224,16 +252,26 @@ __device__ __forceinline__ void traceRefTopology(const SceneView &sv, float3 S, 
 // ---- fast layout -------------------------------------------------------------------------------------------
 // Rays for which the slab test is not monotone in the box (a direction component that is exactly +-0 gives
 // inf*0 = NaN; non-finite origins / directions) take the reference's own exhaustive walk.
-__device__ __forceinline__ bool needsStrictWalk(const SceneView &sv, float3 S, float3 d)
+// 0: ordinary ray.  2: non-finite origin / direction, or an origin so far out that the rounding of S + d*t exceeds what
+// the fast layout's box pad was sized for: the reference's own exhaustive walk.  1: finite ray with a direction component
+// that is zero or denormal (1/d overflows, e.g. the centre column of an axis-aligned camera): the fast layout is still
+// walked — with inv = +-inf a child box is passed iff the ray's coordinate lies strictly inside its slab, entry distances
+// are +-inf and prune correctly, and a NaN (coordinate exactly on a box plane) makes fminf / fmaxf drop the box, which is
+// safe because an acceptable hit point lies strictly inside the padded boxes of its triangle — but a candidate is
+// accepted only if EVERY box on the reference's path to its leaf passes the reference's test (refPathPasses).  An
+// exhaustive walk for these rays cost 1.5 ms PER RAY on a 100 k-triangle scene and set the time of the whole launch.
+__device__ __forceinline__ int rayClass(const SceneView &sv, float3 S, float3 d)
 {
     // 1/d overflows to +-inf for zero AND for denormal components: test the reciprocal itself
     const float3 inv = rcpDir(d);
     const bool inf_rcp = !(fabsf(inv.x) <= 3.4028235e38f) || !(fabsf(inv.y) <= 3.4028235e38f) || !(fabsf(inv.z) <= 3.4028235e38f);
     const float sum = ((S.x + S.y) + S.z) + ((d.x + d.y) + d.z); // inf or NaN anywhere -> not finite
-    // far origins: the rounding of S + d*t grows with |S|, beyond what the fast layout's box pad was sized for
     const bool far = fmaxf(fabsf(S.x), fmaxf(fabsf(S.y), fabsf(S.z))) > sv.strict_origin_limit;
-    return inf_rcp || far || !(fabsf(sum) < 3.0e38f);
+    if (far || !(fabsf(sum) < 3.0e38f))
+        return 2;
+    return inf_rcp ? 1 : 0;
 }
+__device__ __forceinline__ bool needsStrictWalk(const SceneView &sv, float3 S, float3 d) { return rayClass(sv, S, d) != 0; }
 
 // A 128-byte wide node in four 256-bit loads (LDG.E.256, sm_100) instead of seven 128-bit ones: with every lane on
 // a different node the L1 data pipe pays one wavefront per lane per load instruction, and ncu shows that pipe at 73 %
@@ -275,7 +313,8 @@ struct TraceCounters
 // 4-wide walk of the fast layout: while-while (inner nodes until a leaf is reached, then the leaf scan),
 // nearest child first, entry-distance pruning at push and at pop.
 template <bool STATS>
-__device__ __forceinline__ void traceWide(const SceneView &sv, float3 S, float3 d, Hit &hit, TraceCounters *cnt)
+__device__ __forceinline__ void traceWide(const SceneView &sv, float3 S, float3 d, Hit &hit, TraceCounters *cnt,
+                                          bool pathGate = false)
 {
     hit.t = TRT_INF, hit.id = -1, hit.key = 0xFFFFFFFFu;
     if (sv.wide_root == TRT_LINK_EMPTY)
@@ -348,7 +387,7 @@ __device__ __forceinline__ void traceWide(const SceneView &sv, float3 S, float3 
         const int leaf = ~cur;
         if (STATS)
             cnt->leaves++, cnt->tris += (leaf & 7) + 1;
-        scanLeaf<true>(sv, leaf >> 3, (leaf & 7) + 1, S, d, inv, hit);
+        scanLeaf<true>(sv, leaf >> 3, (leaf & 7) + 1, S, d, inv, hit, pathGate);
         StackEntry e;
         do
         {
@@ -474,6 +513,7 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
 {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int kRefillIdle = 8; // refill once this many lanes of the warp are idle
+    constexpr unsigned kPathGateBit = 0x80000000u;
     const int lane = threadIdx.x & 31;
     // per warp: pool of (triangle, t, owner lane) candidates awaiting their inside test, and each lane's best
     // (t bits << 32 | rank) so far
@@ -511,10 +551,11 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                     ray = rays.locate(mine);
                     rays.load(ray, st.S, st.d);
                     st.hit.t = TRT_INF, st.hit.id = -1, st.hit.key = 0xFFFFFFFFu;
-                    if (!sv.use_wide || needsStrictWalk(sv, st.S, st.d))
+                    const int cls = sv.use_wide ? rayClass(sv, st.S, st.d) : 3;
+                    if (cls >= 2 || (POOLED && cls == 1)) // (the pooled inside tests have only the leaf-box gate)
                     {
                         // rare: the reference's own walk, finished on the spot
-                        if (sv.use_wide)
+                        if (cls != 3)
                             traceRefTopology<true>(sv, st.S, st.d, st.hit);
                         else
                             traceRefTopology<false>(sv, st.S, st.d, st.hit);
@@ -525,6 +566,8 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                     {
                         if (POOLED)
                             best[lane] = ((unsigned long long)__float_as_uint(TRT_INF) << 32) | sv.miss_rank;
+                        if (cls == 1)
+                            ray |= kPathGateBit; // tokens stay below 2^31: the top bit marks a class-1 ray (rayClass)
                         st.inv = rcpDir(st.d);
                         stack[0] = packEntry(-1.f, TRT_LINK_EXIT);
                         st.sp = 1;
@@ -569,7 +612,7 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                 if (has)
                 {
                     const int lf = ~st.leaf;
-                    scanLeaf<true>(sv, lf >> 3, (lf & 7) + 1, st.S, st.d, st.inv, st.hit);
+                    scanLeaf<true>(sv, lf >> 3, (lf & 7) + 1, st.S, st.d, st.inv, st.hit, (ray & kPathGateBit) != 0);
                     if (st.cur < 0 && st.cur != TRT_LINK_EXIT)
                     {
                         st.leaf = st.cur; // a second leaf was reached while the first was postponed
@@ -636,10 +679,10 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                 const unsigned long long b = best[lane];
                 st.hit.t = __uint_as_float((unsigned int)(b >> 32));
                 st.hit.id = __ldg(sv.rank_tri + (unsigned int)b);
-                rays.store(ray, st.hit);
+                rays.store(ray & ~kPathGateBit, st.hit);
             }
             else
-                rays.storeFast(sv, ray, st.hit);
+                rays.storeFast(sv, ray & ~kPathGateBit, st.hit);
             ray = 0xffffffffu;
         }
     }
@@ -649,11 +692,12 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
 // scenes without a wide layout.
 __device__ __forceinline__ void traceClosest(const SceneView &sv, float3 S, float3 d, Hit &hit)
 {
-    if (!sv.use_wide)
+    const int cls = sv.use_wide ? rayClass(sv, S, d) : 3;
+    if (cls == 3)
         traceRefTopology<false>(sv, S, d, hit);
-    else if (needsStrictWalk(sv, S, d))
+    else if (cls == 2)
         traceRefTopology<true>(sv, S, d, hit);
     else
-        traceWide<false>(sv, S, d, hit, nullptr);
+        traceWide<false>(sv, S, d, hit, nullptr, cls == 1);
 }
 } // namespace trt

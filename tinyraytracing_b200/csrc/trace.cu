@@ -134,7 +134,7 @@ int launchClosest(trt_scene *s, const float *d_rays6, size_t n, int32_t *d_id, f
         k_closest<1><<<grid, kTraceBlock, 0, stream>>>(s->view, d_rays6, n, d_id, d_t);
     else if (flags & TRT_TRACE_REFTOPO)
         k_closest<0><<<grid, kTraceBlock, 0, stream>>>(s->view, d_rays6, n, d_id, d_t);
-    else if ((flags & TRT_TRACE_PLAIN) || n > 0xfffffff0ull)
+    else if ((flags & TRT_TRACE_PLAIN) || n > 0x7fffffffull) // the walker's ray tokens are 31-bit (top bit: class-1 mark)
         k_closest<2><<<grid, kTraceBlock, 0, stream>>>(s->view, d_rays6, n, d_id, d_t);
     else
     {

@@ -378,7 +378,8 @@ def run_gpu(args):
             if rank == 0 and world == 1:
                 out["cornell_standin"] = standin_measurements(args)
         if rank == 0 and world == 1 and not args.no_cpu:
-            out["cpu_baseline"] = cpu_baseline(f, rays)
+            t_host = np.ctypeslib.as_array(C.cast(p_t, C.POINTER(C.c_float)), (n,))
+            out["cpu_baseline"] = cpu_baseline(f, rays, ids_host, t_host, host)
         if args.extra and rank == 0 and world == 1:
             out["extra"] = extra_measurements(args, tmp)
         for p in (p_rays, p_id, p_t):
@@ -402,8 +403,10 @@ def layout_roofline(dev, rays, n, ms_per_step, peak):
             "note": "served from L1 (hit rate ~90 %): the kernel is issue / L1-latency bound, see profiles/"}
 
 
-def cpu_baseline(files, rays):
-    """The unmodified reference traversal (oracle/_ref) on the host cores, bounded sample of the same rays."""
+def cpu_baseline(files, rays, gpu_ids=None, gpu_t=None, host=None):
+    """The unmodified reference traversal (oracle/_ref) on the host cores, bounded sample of the same rays.  The same
+    pass doubles as BASELINE config 2's check on the bench's own batch: the GPU's triangle ids and distance bits (from
+    the timed e2e leg) against what the reference's traverseBVH returned for every ray of the sample."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     cores = os.cpu_count() or 1
     import refbridge
@@ -416,22 +419,38 @@ def cpu_baseline(files, rays):
             ref = refbridge.RefScene(files["xml"], files["obj"], files["mtl"], files["basedir"])
         finally:
             os.dup2(saved, 1)
-        trace, kind = (lambda r: ref.trace(r, threads=cores)), "reference"
+        trace, kind = (lambda r: ref.trace(r, threads=cores)), "reference"  # -> (t, canonical post-build id)
     else:
         import oraclelib
 
         orc = oraclelib.OracleScene(oraclelib.parsed_scene(SCENE, 512, 512))
-        trace, kind = (lambda r: orc.trace(r, threads=cores)), "port"
+        trace, kind = (lambda r: orc.trace(r, threads=cores)[::-1]), "port"  # the oracle returns (id, t)
     pilot = rays[: 1 << 18]
     t0 = time.perf_counter()
     trace(pilot)
     rate = len(pilot) / (time.perf_counter() - t0)
     n = int(min(len(rays), max(1 << 18, rate * 10.0)))  # about 10 s of CPU work
     t0 = time.perf_counter()
-    trace(rays[:n])
+    ref_t, ref_id = trace(rays[:n])
     dt = time.perf_counter() - t0
-    return {"value": n / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind,
-            "sample": "first %d rays of the %d-ray batch, %d OpenMP threads" % (n, len(rays), cores)}
+    out = {"value": n / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind,
+           "sample": "first %d rays of the %d-ray batch, %d OpenMP threads" % (n, len(rays), cores)}
+    if gpu_ids is not None and gpu_t is not None:
+        ids, t = np.asarray(gpu_ids[:n]), np.asarray(gpu_t[:n])
+        same = ids == np.asarray(ref_id)
+        if host is not None and not same.all():
+            # the reference identifies a triangle by content: geometrically identical triangles are one identity
+            v = host.triangles()["v"]
+            bad = np.flatnonzero(~same)
+            both = (ids[bad] >= 0) & (np.asarray(ref_id)[bad] >= 0)
+            eq = np.zeros(len(bad), bool)
+            eq[both] = (v[ids[bad][both]] == v[np.asarray(ref_id)[bad][both]]).all(axis=1)
+            same[bad] = eq
+        out["parity"] = {"rays_compared": int(n), "triangle_ids_equal": bool(same.all()),
+                         "id_mismatches": int((~same).sum()),
+                         "distance_bits_equal": bool(np.array_equal(t.view(np.uint32), np.asarray(ref_t).view(np.uint32))),
+                         "against": "the unmodified reference traverseBVH" if kind == "reference" else "the oracle port"}
+    return out
 
 
 def render_measurements(args, tmp, rank, world, local, barrier):

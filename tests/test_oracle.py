@@ -187,3 +187,43 @@ def test_closed_form_barycentrics_give_the_reference_pn(name, oracle_scenes):
     ok = np.isfinite(g["pn"][hit]).all(axis=1) & np.isfinite(mine).all(axis=1)
     assert ok.sum() > 1000
     assert np.abs(mine[ok] - g["pn"][hit][ok]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_oracle_matches_the_live_reference_including_nan_slabs(name, oracle_scenes, host_scenes, scene_files):
+    """Tier B against tier A LIVE (oracle/_ref/libref.so = the unmodified reference sources, built in the build
+    container): the config-2 ray population plus the rays whose treatment rests on the reference's NaN behaviour —
+    zero / denormal direction components (1/d = +-inf) with an origin coordinate exactly on a node box plane, so that
+    (b - S) * inf = NaN inside interactAABB (bvh.cpp:231-245) and glm's min / max decide.  The GPU path is validated
+    against the oracle on the same kind of rays (tests/test_gpu_closest.py); this test pins the oracle's side."""
+    import refbridge
+    from conftest import make_rays
+
+    if not refbridge.available():
+        pytest.skip("oracle/_ref/libref.so not built")
+    f = scene_files[name]
+    ref = refbridge.RefScene(f["xml"], f["obj"], f["mtl"], f["basedir"])
+    orc, host = oracle_scenes[name], host_scenes[name]
+    rays = make_rays(host, orc, 60000, seed=23)
+    boxes, _ = host.nodes()
+    lo, hi = host.root_box()
+    rng = np.random.default_rng(29)
+    n = 40000
+    o = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    axis = rng.integers(0, 3, n)
+    d[np.arange(n), axis] = rng.choice(np.array([0.0, -0.0, 1e-42, -1e-42], np.float32), n)
+    pick, side = rng.integers(0, len(boxes), n), rng.integers(0, 2, n)
+    plane = boxes[pick, axis + 3 * side]
+    on_plane = (rng.random(n) < 0.5) & np.isfinite(plane)
+    o[on_plane, axis[on_plane]] = plane[on_plane]
+    rays = np.concatenate([rays, np.concatenate([o, d], 1)]).astype(np.float32)
+    rt, rid = ref.trace(rays)
+    oid, ot = orc.trace(rays)
+    assert np.array_equal(ot.view(np.uint32), rt.view(np.uint32))
+    assert np.array_equal(oid >= 0, rid >= 0) and (oid >= 0).sum() > 20000
+    # the reference identifies a triangle by content (geometrically identical triangles are one identity)
+    v = host.triangles()["v"]
+    hit = oid >= 0
+    assert np.array_equal(v[oid[hit]], v[rid[hit]])

@@ -26,6 +26,13 @@ int trt_host_scene_from_arrays(int32_t n_tris, const float *v9, const float *vn9
                                const float *eye, const float *lookat, const float *up, double fovy, int32_t width,
                                int32_t height, int leaf_num, trt_host_scene **out);
 
+/* Binary scene cache: everything trt_host_scene_desc / _faces / _material_name return — the parsed
+ * OBJ / MTL / XML, the decoded textures and the buildBVH topology (scene.cpp:3-213, bvh.cpp:16-144 never run again) — in
+ * one file with a format version and a checksum.  trt_host_scene_load_cache gives a scene that is bit-identical in
+ * every array to the one that was saved; a truncated, corrupted or foreign file is an error, never a partial scene. */
+int trt_host_scene_save(trt_host_scene *s, const char *path);
+int trt_host_scene_load_cache(const char *path, trt_host_scene **out);
+
 /* POD view (valid until trt_host_scene_free); feed it to trt_scene_create. */
 const trt_scene_desc *trt_host_scene_desc(trt_host_scene *s);
 /* post-build triangle index -> ordinal of the OBJ `f` statement (or input index for from_arrays) */

@@ -227,3 +227,47 @@ def test_tree_optimisation_is_deterministic_and_never_worse(host_scenes, monkeyp
         assert off["violations"] == 0 and off["n_fast_tris"] == a["n_fast_tris"]
         assert a["sah_wide"] <= off["sah_wide"] * (1 + 1e-12)
     monkeypatch.delenv("TRT_REINSERT", raising=False)
+
+
+# ---- binary scene cache (trt_host_scene_save / trt_host_scene_load_cache) ----------------------------
+def _same_scene(a, b):
+    ta, tb = a.triangles(), b.triangles()
+    assert all(np.array_equal(ta[k].view(np.uint8), tb[k].view(np.uint8)) for k in ta)
+    (ba, la), (bb, lb) = a.nodes(), b.nodes()
+    assert np.array_equal(bits(ba), bits(bb)) and np.array_equal(la, lb)
+    assert a.material_names() == b.material_names() and a.materials() == b.materials()
+    for x, y in zip(a.lights(), b.lights()):
+        if isinstance(x, np.ndarray):
+            assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+        else:
+            assert x == y
+    ca, cb = a.camera(), b.camera()
+    assert all(np.array_equal(np.asarray(ca[k]), np.asarray(cb[k])) for k in ca)
+    assert a.layout_check() == b.layout_check()
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_scene_cache_roundtrip_is_bit_identical(name, host_scenes, tmp_path):
+    p = str(tmp_path / (name + ".trtscn"))
+    host_scenes[name].save(p)
+    back = trt.HostScene.load_cache(p)
+    _same_scene(host_scenes[name], back)
+    ta, tb = host_scenes[name].textures(), back.textures()
+    assert len(ta) == len(tb) == (3 if name == "staircase" else 0)  # decoded textures travel with the cache
+    assert all(np.array_equal(x, y) for x, y in zip(ta, tb))
+    back.close()
+
+
+def test_scene_cache_rejects_damaged_files(host_scenes, tmp_path):
+    p = str(tmp_path / "v.trtscn")
+    host_scenes["veach-mis"].save(p)
+    raw = open(p, "rb").read()
+    cases = {"truncated": raw[: len(raw) // 2], "one flipped bit": raw[:1000] + bytes([raw[1000] ^ 1]) + raw[1001:],
+             "foreign file": b"P6 1 1 255 " + bytes(64), "empty": b"", "wrong version": raw[:8] + bytes([9]) + raw[9:]}
+    for what, data in cases.items():
+        q = str(tmp_path / "bad.trtscn")
+        open(q, "wb").write(data)
+        with pytest.raises(trt.TrtError):
+            trt.HostScene.load_cache(q)
+    with pytest.raises(trt.TrtError):
+        trt.HostScene.load_cache(str(tmp_path / "missing.trtscn"))

@@ -73,7 +73,7 @@ EXPORTS = ["trt_device_count", "trt_scene_create", "trt_scene_destroy", "trt_hos
            "trt_render_accumulate", "trt_resolve", "trt_layout_check", "trt_get_stats", "trt_reset_stats", "trt_last_error",
            "trt_version", "trt_host_scene_load", "trt_host_scene_from_arrays", "trt_host_scene_desc",
            "trt_host_scene_faces", "trt_host_scene_material_name", "trt_host_scene_build_seconds",
-           "trt_host_scene_free", "trt_decode_jpeg", "trt_write_png"]
+           "trt_host_scene_free", "trt_host_scene_save", "trt_host_scene_load_cache", "trt_decode_jpeg", "trt_write_png"]
 
 
 def library_path():
@@ -124,6 +124,8 @@ def load_library():
     L.trt_host_scene_build_seconds.restype = C.c_double
     L.trt_host_scene_build_seconds.argtypes = [vp]
     L.trt_host_scene_free.argtypes = [vp]
+    L.trt_host_scene_save.argtypes = [vp, cp]
+    L.trt_host_scene_load_cache.argtypes = [cp, C.POINTER(vp)]
     L.trt_host_scene_free.restype = None
     L.trt_write_png.argtypes = [cp, i32, i32, vp, C.c_int]
     L.trt_decode_jpeg.argtypes = [cp, C.POINTER(i32), C.POINTER(i32), vp, sz]
@@ -160,6 +162,16 @@ class HostScene:
         self.h = handle
         self.lib = load_library()
         self.desc = self.lib.trt_host_scene_desc(self.h).contents
+
+    def save(self, path):
+        """Binary scene cache (trt_host_scene_save): parsed scene + decoded textures + buildBVH topology in one file."""
+        _check(self.lib.trt_host_scene_save(self.h, path.encode()), "trt_host_scene_save")
+
+    @classmethod
+    def load_cache(cls, path):
+        h = C.c_void_p()
+        _check(load_library().trt_host_scene_load_cache(path.encode(), C.byref(h)), "trt_host_scene_load_cache")
+        return cls(h)
 
     def layout_check(self):
         """Builds the GPU layouts on the host and verifies their invariants (trt_layout_check, no device needed)."""

@@ -4,7 +4,10 @@
 #include "../../../include/trt_host.h"
 
 #include <chrono>
+#include <cstdio>
 #include <cstring>
+#include <memory>
+#include <vector>
 
 namespace trt
 {
@@ -31,6 +34,80 @@ int finish(std::unique_ptr<trt_host_scene> &s, int leaf_num, trt_host_scene **ou
     *out = s.release();
     return TRT_OK;
 }
+} // namespace
+
+// ---- binary scene cache ------------------------------------------------------------------------------------------
+// Layout: 8-byte magic, u32 version, u32 sizeof(trt_material), then a sequence of length-prefixed sections (u64 byte
+// count + raw little-endian data) in a fixed order, then the FNV-1a 64 hash of everything before it.
+namespace
+{
+const char kCacheMagic[8] = {'T', 'R', 'T', 'S', 'C', 'N', '0', '1'};
+const uint32_t kCacheVersion = 1;
+
+// FNV-1a over 64-bit words (bytes for the tail) of one chunk; the file hash chains the chunk hashes in file order
+uint64_t chunkHash(const void *p, size_t n)
+{
+    const unsigned char *b = static_cast<const unsigned char *>(p);
+    uint64_t h = 1469598103934665603ull;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8)
+    {
+        uint64_t w;
+        std::memcpy(&w, b + i, 8);
+        h = (h ^ w) * 1099511628211ull;
+    }
+    for (; i < n; ++i)
+        h = (h ^ b[i]) * 1099511628211ull;
+    return h ^ (uint64_t)n;
+}
+
+struct CacheWriter
+{
+    FILE *fp;
+    uint64_t hash = 1469598103934665603ull;
+    bool ok = true;
+    void raw(const void *p, size_t n)
+    {
+        hash = (hash ^ chunkHash(p, n)) * 1099511628211ull;
+        ok = ok && (n == 0 || std::fwrite(p, 1, n, fp) == n);
+    }
+    void section(const void *p, size_t n)
+    {
+        const uint64_t len = n;
+        raw(&len, 8);
+        raw(p, n);
+    }
+    template <typename T>
+    void vec(const std::vector<T> &v) { section(v.data(), v.size() * sizeof(T)); }
+};
+
+struct CacheReader // hashes what it reads, chunk by chunk, exactly as CacheWriter::raw did
+{
+    const unsigned char *p, *end;
+    uint64_t hash = 1469598103934665603ull;
+    bool take(void *dst, size_t n)
+    {
+        if ((size_t)(end - p) < n)
+            return false;
+        std::memcpy(dst, p, n);
+        hash = (hash ^ chunkHash(p, n)) * 1099511628211ull;
+        p += n;
+        return true;
+    }
+    template <typename T>
+    bool vec(std::vector<T> &v)
+    {
+        uint64_t len = 0;
+        if (!take(&len, 8) || len % sizeof(T) != 0 || (uint64_t)(end - p) < len)
+            return false;
+        v.resize(len / sizeof(T));
+        if (len)
+            std::memcpy(v.data(), p, len);
+        hash = (hash ^ chunkHash(p, len)) * 1099511628211ull;
+        p += len;
+        return true;
+    }
+};
 } // namespace
 
 extern "C"
@@ -133,6 +210,153 @@ int trt_host_scene_from_arrays(int32_t n, const float *v9, const float *vn9, con
     {
         trt::setLastError(e.what());
         return TRT_ERR_INVALID;
+    }
+}
+
+int trt_host_scene_save(trt_host_scene *s, const char *path)
+{
+    if (!s || !path)
+    {
+        trt::setLastError("trt_host_scene_save: null argument");
+        return TRT_ERR_INVALID;
+    }
+    FILE *fp = std::fopen(path, "wb");
+    if (!fp)
+    {
+        trt::setLastError(std::string("trt_host_scene_save: cannot open ") + path);
+        return TRT_ERR_INVALID;
+    }
+    const trt::SceneArrays &a = *s->arrays;
+    CacheWriter w{fp};
+    const uint32_t head[2] = {kCacheVersion, (uint32_t)sizeof(trt_material)};
+    w.raw(kCacheMagic, 8);
+    w.raw(head, 8);
+    w.vec(a.v), w.vec(a.vn), w.vec(a.vt), w.vec(a.normal), w.vec(a.mtl), w.vec(a.face);
+    w.vec(a.node_box), w.vec(a.node_link);
+    w.vec(a.materials), w.vec(a.lights);
+    w.vec(a.light_v), w.vec(a.light_vn), w.vec(a.light_cum_area);
+    std::vector<int32_t> meta = {(int32_t)a.material_names.size(), (int32_t)a.texture_images.size(), a.desc.width, a.desc.height};
+    w.vec(meta);
+    for (const std::string &n : a.material_names)
+        w.section(n.data(), n.size());
+    for (const trt::Image &im : a.texture_images)
+    {
+        const int32_t rc[2] = {im.rows, im.cols};
+        w.section(rc, 8);
+        w.section(im.data->data(), im.data->size());
+    }
+    float cam[12];
+    std::memcpy(cam, a.desc.eye, 12), std::memcpy(cam + 3, a.desc.lower_left_corner, 12);
+    std::memcpy(cam + 6, a.desc.horizontal, 12), std::memcpy(cam + 9, a.desc.vertical, 12);
+    w.section(cam, sizeof cam);
+    const uint64_t h = w.hash;
+    const bool ok = w.ok && std::fwrite(&h, 1, 8, fp) == 8;
+    if (std::fclose(fp) != 0 || !ok)
+    {
+        trt::setLastError(std::string("trt_host_scene_save: write failed: ") + path);
+        return TRT_ERR_INVALID;
+    }
+    return TRT_OK;
+}
+
+int trt_host_scene_load_cache(const char *path, trt_host_scene **out)
+{
+    if (!path || !out)
+    {
+        trt::setLastError("trt_host_scene_load_cache: null argument");
+        return TRT_ERR_INVALID;
+    }
+    auto fail = [&](const std::string &why) {
+        trt::setLastError("trt_host_scene_load_cache: " + why + ": " + path);
+        return TRT_ERR_INVALID;
+    };
+    FILE *fp = std::fopen(path, "rb");
+    if (!fp)
+        return fail("cannot open");
+    std::vector<unsigned char> buf;
+    std::fseek(fp, 0, SEEK_END);
+    const long size = std::ftell(fp);
+    std::fseek(fp, 0, SEEK_SET);
+    if (size < 24)
+    {
+        std::fclose(fp);
+        return fail("not a scene cache");
+    }
+    buf.resize((size_t)size);
+    const bool rd = std::fread(buf.data(), 1, buf.size(), fp) == buf.size();
+    std::fclose(fp);
+    if (!rd)
+        return fail("read failed");
+    if (std::memcmp(buf.data(), kCacheMagic, 8) != 0)
+        return fail("not a scene cache");
+    uint64_t stored = 0;
+    std::memcpy(&stored, buf.data() + buf.size() - 8, 8);
+    CacheReader r{buf.data(), buf.data() + buf.size() - 8};
+    char magic[8];
+    uint32_t head[2] = {0, 0};
+    if (!r.take(magic, 8) || !r.take(head, 8) || head[0] != kCacheVersion || head[1] != sizeof(trt_material))
+        return fail("unsupported cache version");
+    try
+    {
+        std::unique_ptr<trt_host_scene> s(new trt_host_scene());
+        s->arrays.reset(new trt::SceneArrays());
+        trt::SceneArrays &a = *s->arrays;
+        std::vector<int32_t> meta;
+        bool ok = r.vec(a.v) && r.vec(a.vn) && r.vec(a.vt) && r.vec(a.normal) && r.vec(a.mtl) && r.vec(a.face) &&
+                  r.vec(a.node_box) && r.vec(a.node_link) && r.vec(a.materials) && r.vec(a.lights) && r.vec(a.light_v) &&
+                  r.vec(a.light_vn) && r.vec(a.light_cum_area) && r.vec(meta) && meta.size() == 4 && meta[0] >= 0 && meta[1] >= 0;
+        for (int i = 0; ok && i < meta[0]; ++i)
+        {
+            std::vector<char> name;
+            ok = r.vec(name);
+            a.material_names.emplace_back(name.begin(), name.end());
+        }
+        for (int i = 0; ok && i < meta[1]; ++i)
+        {
+            std::vector<int32_t> rc;
+            trt::Image im;
+            im.data = std::make_shared<std::vector<unsigned char>>();
+            ok = r.vec(rc) && rc.size() == 2 && r.vec(*im.data) && rc[0] >= 1 && rc[1] >= 1 &&
+                 im.data->size() == (size_t)rc[0] * rc[1] * 3;
+            if (ok)
+            {
+                im.rows = rc[0], im.cols = rc[1];
+                a.texture_images.push_back(im);
+                a.textures.push_back(trt_texture{im.rows, im.cols, im.data->data()});
+            }
+        }
+        std::vector<float> cam;
+        ok = ok && r.vec(cam) && cam.size() == 12 && r.p == r.end;
+        if (!ok || r.hash != stored) // nothing read so far is used before this check
+            return fail("checksum mismatch or malformed file (truncated, corrupted or foreign)");
+        // consistency of the sections with each other (a valid checksum only says the file is what was written)
+        const size_t n = a.mtl.size();
+        ok = ok && a.v.size() == n * 9 && a.vn.size() == n * 9 && a.vt.size() == n * 6 && a.normal.size() == n * 3 &&
+             a.face.size() == n && a.node_link.size() % 4 == 0 && a.node_box.size() == a.node_link.size() / 4 * 6 &&
+             a.light_v.size() == a.light_cum_area.size() * 9 && a.light_vn.size() == a.light_v.size() &&
+             a.material_names.size() == a.materials.size();
+        if (!ok)
+            return fail("malformed cache");
+        trt_scene_desc &d = a.desc;
+        std::memset(&d, 0, sizeof d);
+        d.n_tris = (int)n;
+        d.v = a.v.data(), d.vn = a.vn.data(), d.vt = a.vt.data(), d.normal = a.normal.data(), d.mtl = a.mtl.data();
+        d.n_nodes = (int)(a.node_link.size() / 4);
+        d.node_box = a.node_box.data(), d.node_link = a.node_link.data();
+        d.n_materials = (int)a.materials.size(), d.materials = a.materials.data();
+        d.n_lights = (int)a.lights.size(), d.lights = a.lights.data();
+        d.n_light_tris = (int)a.light_cum_area.size();
+        d.light_v = a.light_v.data(), d.light_vn = a.light_vn.data(), d.light_cum_area = a.light_cum_area.data();
+        d.n_textures = (int)a.textures.size(), d.textures = a.textures.data();
+        std::memcpy(d.eye, cam.data(), 12), std::memcpy(d.lower_left_corner, cam.data() + 3, 12);
+        std::memcpy(d.horizontal, cam.data() + 6, 12), std::memcpy(d.vertical, cam.data() + 9, 12);
+        d.width = meta[2], d.height = meta[3];
+        *out = s.release();
+        return TRT_OK;
+    }
+    catch (const std::exception &e)
+    {
+        return fail(e.what());
     }
 }
 

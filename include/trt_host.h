@@ -48,6 +48,11 @@ int trt_decode_jpeg(const char *path, int32_t *rows, int32_t *cols, uint8_t *bgr
 /* Uncompressed 8-bit RGB(A) PNG, the role svpng.inc:77-108 plays in the reference (main.cpp:40). */
 int trt_write_png(const char *path, int32_t w, int32_t h, const uint8_t *rgb, int alpha);
 
+/* The LINEAR image (the double[W*H*3] buffer of main.cpp:74, before imshow's gamma and 8-bit quantisation) as a
+ * 32-bit float PFM file ("PF", little-endian, rows bottom-to-top as the format prescribes): the reference can only
+ * write the quantised PNG, which is useless for comparing renders numerically. */
+int trt_write_pfm(const char *path, int32_t w, int32_t h, const double *rgb_linear);
+
 #ifdef __cplusplus
 }
 #endif

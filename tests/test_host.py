@@ -271,3 +271,17 @@ def test_scene_cache_rejects_damaged_files(host_scenes, tmp_path):
             trt.HostScene.load_cache(q)
     with pytest.raises(trt.TrtError):
         trt.HostScene.load_cache(str(tmp_path / "missing.trtscn"))
+
+
+def test_pfm_writer_keeps_the_linear_image(tmp_path):
+    """trt_write_pfm: the double[W*H*3] buffer of main.cpp:74 as 32-bit floats, rows bottom-to-top (PFM convention)."""
+    rng = np.random.default_rng(1)
+    img = rng.uniform(0, 40, (23, 31, 3))  # linear radiance, well above 1
+    p = str(tmp_path / "x.pfm")
+    assert trt.load_library().trt_write_pfm(p.encode(), 31, 23, np.ascontiguousarray(img).ctypes.data) == 0
+    raw = open(p, "rb").read()
+    head, rest = raw.split(b"\n", 3)[:3], raw.split(b"\n", 3)[3]
+    assert head == [b"PF", b"31 23", b"-1.0"]
+    back = np.frombuffer(rest, "<f4").reshape(23, 31, 3)[::-1]
+    assert np.array_equal(back, img.astype(np.float32))
+    assert trt.load_library().trt_write_pfm(p.encode(), 0, 23, np.ascontiguousarray(img).ctypes.data) != 0

@@ -73,7 +73,7 @@ EXPORTS = ["trt_device_count", "trt_scene_create", "trt_scene_destroy", "trt_hos
            "trt_render_accumulate", "trt_resolve", "trt_layout_check", "trt_get_stats", "trt_reset_stats", "trt_last_error",
            "trt_version", "trt_host_scene_load", "trt_host_scene_from_arrays", "trt_host_scene_desc",
            "trt_host_scene_faces", "trt_host_scene_material_name", "trt_host_scene_build_seconds",
-           "trt_host_scene_free", "trt_host_scene_save", "trt_host_scene_load_cache", "trt_decode_jpeg", "trt_write_png"]
+           "trt_host_scene_free", "trt_host_scene_save", "trt_host_scene_load_cache", "trt_decode_jpeg", "trt_write_png", "trt_write_pfm"]
 
 
 def library_path():
@@ -128,6 +128,7 @@ def load_library():
     L.trt_host_scene_load_cache.argtypes = [cp, C.POINTER(vp)]
     L.trt_host_scene_free.restype = None
     L.trt_write_png.argtypes = [cp, i32, i32, vp, C.c_int]
+    L.trt_write_pfm.argtypes = [cp, i32, i32, vp]
     L.trt_decode_jpeg.argtypes = [cp, C.POINTER(i32), C.POINTER(i32), vp, sz]
     _lib = L
     return L

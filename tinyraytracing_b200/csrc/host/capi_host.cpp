@@ -399,6 +399,34 @@ int trt_decode_jpeg(const char *path, int32_t *rows, int32_t *cols, uint8_t *bgr
     return TRT_OK;
 }
 
+int trt_write_pfm(const char *path, int32_t w, int32_t h, const double *rgb_linear)
+{
+    if (!path || !rgb_linear || w < 1 || h < 1)
+    {
+        trt::setLastError("trt_write_pfm: bad argument");
+        return TRT_ERR_INVALID;
+    }
+    FILE *fp = std::fopen(path, "wb");
+    if (!fp)
+    {
+        trt::setLastError(std::string("cannot open ") + path);
+        return TRT_ERR_INVALID;
+    }
+    bool ok = std::fprintf(fp, "PF\n%d %d\n-1.0\n", w, h) > 0; // negative scale = little-endian
+    std::vector<float> row((size_t)w * 3);
+    for (int y = h - 1; ok && y >= 0; --y) // PFM stores the bottom row first
+    {
+        const double *src = rgb_linear + (size_t)y * w * 3;
+        for (size_t i = 0; i < row.size(); ++i)
+            row[i] = (float)src[i];
+        ok = std::fwrite(row.data(), sizeof(float), row.size(), fp) == row.size();
+    }
+    ok = (std::fclose(fp) == 0) && ok;
+    if (!ok)
+        trt::setLastError(std::string("trt_write_pfm: write failed: ") + path);
+    return ok ? TRT_OK : TRT_ERR_INVALID;
+}
+
 int trt_write_png(const char *path, int32_t w, int32_t h, const uint8_t *rgb, int alpha)
 {
     FILE *fp = std::fopen(path, "wb");

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--max-depth", type=int, default=0, help="0 = reference behaviour (Russian roulette only)")
     ap.add_argument("--out", default="image.png")
+    ap.add_argument("--pfm", default=None, help="also write the linear (pre-gamma) image as a 32-bit float PFM file")
     a = ap.parse_args()
     if bool(a.scene) == bool(a.files):
         ap.error("give exactly one of --scene / --files")
@@ -60,6 +61,9 @@ def main():
             g = np.power(img, np.float64(np.float32(1.0) / np.float32(2.2))) * 255  # imshow, main.cpp:30-38
             rgb = np.ascontiguousarray(np.minimum(np.maximum(g, 0.0), 255.0).astype(np.uint8))
             trt.load_library().trt_write_png(a.out.encode(), rgb.shape[1], rgb.shape[0], rgb.ctypes.data, 0)
+            if a.pfm:  # the linear buffer, for numerical comparison of renders
+                lin = np.ascontiguousarray(img, np.float64)
+                trt.load_library().trt_write_pfm(a.pfm.encode(), lin.shape[1], lin.shape[0], lin.ctypes.data)
             st = dev.stats()
             print("%dx%d, %d spp on %d GPU(s): %.2f s, wrote %s (this rank: %d closest + %d shadow rays)" % (
                 rgb.shape[1], rgb.shape[0], a.spp, world, dt, a.out, st["rays_closest"], st["rays_shadow"]))

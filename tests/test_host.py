@@ -285,3 +285,17 @@ def test_pfm_writer_keeps_the_linear_image(tmp_path):
     back = np.frombuffer(rest, "<f4").reshape(23, 31, 3)[::-1]
     assert np.array_equal(back, img.astype(np.float32))
     assert trt.load_library().trt_write_pfm(p.encode(), 0, 23, np.ascontiguousarray(img).ctypes.data) != 0
+
+
+def test_optimal_collapse_keeps_the_invariants_and_never_costs_more(host_scenes, monkeypatch):
+    """TRT_COLLAPSE=optimal (experimental): the dynamic-programming collapse must give a valid layout whose summed
+    child-box area is at most the greedy collapse's."""
+    for name in SCENES:
+        monkeypatch.delenv("TRT_COLLAPSE", raising=False)
+        greedy = host_scenes[name].layout_check()
+        monkeypatch.setenv("TRT_COLLAPSE", "optimal")
+        opt = host_scenes[name].layout_check()
+        assert opt["violations"] == 0 and opt["n_fast_tris"] == greedy["n_fast_tris"]
+        assert opt["sah_wide"] <= greedy["sah_wide"] * (1 + 1e-6)
+        assert opt["wide_nodes"] <= greedy["wide_nodes"]
+    monkeypatch.delenv("TRT_COLLAPSE", raising=False)

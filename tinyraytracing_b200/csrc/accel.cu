@@ -2,9 +2,11 @@
 #include "accel.h"
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cmath>
 #include <future>
+#include <memory>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -495,6 +497,78 @@ double collapseCost(const std::vector<BNode> &bn, int *depth_out)
     *depth_out = maxDepth;
     return sum;
 }
+
+// Optimal 4-wide collapse by dynamic programming (after Ylitie, Karras, Laine 2017, "Efficient incoherent ray traversal
+// on GPUs through compressed wide BVHs", §3.1), for the measure collapseCost uses: the summed surface area of all child
+// boxes.  S[x] = cost of binary node x occupying one child slot (its own box + the best 4 slots below it, if inner);
+// G[x][k] = cheapest cover of x's subtree with at most k slots; F[x][k] = the same when x itself may not be a slot.
+// EXPERIMENTAL (TRT_COLLAPSE=optimal): the host-side figure improves by 0.2-7 % over the greedy collapse; unmeasured
+// on the GPU so far, hence not the default.
+struct OptimalCollapse
+{
+    const std::vector<BNode> &bn;
+    std::vector<float> S;
+    std::vector<std::array<float, 5>> F, G;
+
+    explicit OptimalCollapse(const std::vector<BNode> &b, int32_t used) : bn(b), S(used, 0.f), F(used), G(used)
+    {
+        std::vector<int32_t> order, st{0};
+        while (!st.empty())
+        {
+            const int32_t i = st.back();
+            st.pop_back();
+            order.push_back(i);
+            if (bn[i].right != -2)
+                st.push_back(bn[i].left), st.push_back(bn[i].right);
+        }
+        for (size_t oi = order.size(); oi-- > 0;)
+        {
+            const int32_t x = order[oi];
+            const float a = halfArea(bn[x].lo, bn[x].hi);
+            if (bn[x].right == -2)
+            {
+                S[x] = a;
+                for (int k = 1; k <= 4; ++k)
+                    G[x][k] = a, F[x][k] = INFINITY;
+                continue;
+            }
+            const int32_t l = bn[x].left, r = bn[x].right;
+            F[x][1] = INFINITY;
+            for (int k = 2; k <= 4; ++k)
+            {
+                float best = INFINITY;
+                for (int i = 1; i < k; ++i)
+                    best = std::fmin(best, G[l][i] + G[r][k - i]);
+                F[x][k] = best;
+            }
+            S[x] = a + F[x][4];
+            G[x][1] = S[x];
+            for (int k = 2; k <= 4; ++k)
+                G[x][k] = std::fmin(S[x], F[x][k]);
+        }
+    }
+    // the binary nodes that become the slots covering y's subtree with at most k slots
+    void cover(int32_t y, int k, int32_t *slots, int &n) const
+    {
+        if (k == 1 || bn[y].right == -2 || !(F[y][k] < S[y]))
+        {
+            slots[n++] = y;
+            return;
+        }
+        split(y, k, slots, n);
+    }
+    // y itself is not a slot: distribute k slots over its two children
+    void split(int32_t y, int k, int32_t *slots, int &n) const
+    {
+        const int32_t l = bn[y].left, r = bn[y].right;
+        int bi = 1;
+        for (int i = 1; i < k; ++i)
+            if (G[l][i] + G[r][k - i] < G[l][bi] + G[r][k - bi])
+                bi = i;
+        cover(l, bi, slots, n);
+        cover(r, k - bi, slots, n);
+    }
+};
 } // namespace
 
 std::string buildWide(const trt_scene_desc &desc, AccelBuild &out)
@@ -685,6 +759,12 @@ std::string buildWide(const trt_scene_desc &desc, AccelBuild &out)
         int32_t bnode, wide, depth;
     };
     std::vector<Item> todo;
+    std::unique_ptr<OptimalCollapse> optimal;
+    {
+        const char *cenv = getenv("TRT_COLLAPSE");
+        if (cenv && std::string(cenv) == "optimal" && prims.size() <= 4000000)
+            optimal.reset(new OptimalCollapse(bn, wb.next.load()));
+    }
     out.wide_nodes.emplace_back();
     todo.push_back({0, 0, 1});
     int maxDepth = 1;
@@ -697,7 +777,12 @@ std::string buildWide(const trt_scene_desc &desc, AccelBuild &out)
         maxDepth = it.depth > maxDepth ? it.depth : maxDepth;
         int32_t kids[4] = {bn[it.bnode].left, bn[it.bnode].right, -1, -1};
         int nk = 2;
-        while (nk < 4)
+        if (optimal)
+        {
+            nk = 0;
+            optimal->split(it.bnode, 4, kids, nk);
+        }
+        while (!optimal && nk < 4)
         {
             int pick = -1;
             float best = -1.f;

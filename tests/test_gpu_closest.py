@@ -51,7 +51,7 @@ def test_hit_attributes(name, host_scenes, oracle_scenes, device_scenes):
     hit = ids >= 0
     assert np.array_equal(hp[hit].view(np.uint32), ohp[hit].view(np.uint32))  # S + d*t in float: bit-exact
     ok = np.isfinite(opn[hit]).all(axis=1)
-    # pn goes through a double least-squares solve (Eigen QR in the reference): same algorithm, tolerance 1e-6
+    # pn goes through a double least-squares solve (Eigen QR in the reference, closed form on the device): tolerance 1e-6
     assert np.abs(pn[hit][ok] - opn[hit][ok]).max() <= 1e-6
     assert (~hit).sum() == 0 or (np.all(hp[~hit] == 0) and np.all(pn[~hit] == 0))  # HitRecord defaults on a miss
 

@@ -615,7 +615,7 @@ std::string buildWide(const trt_scene_desc &desc, AccelBuild &out)
 
     // Own boxes are padded by 256 ulp(scene scale), scale = largest |coordinate| of the reference leaf boxes.  A
     // reported hit point S + d*t lies within a few ulp(|S| + t) of its (non-sliver) triangle, and rays whose origin
-    // is farther than 4 * scale from the coordinate origin take the strict walk, so the ray passes the padded box of
+    // is farther than 4 * scale from the coordinate origin take the exhaustive walk, so the ray passes the padded box of
     // every triangle it can hit with a margin of well over ten times the rounding of the slab test.
     // A pad tied to the scale rather than a fixed length matters for finely tessellated geometry: staircase has
     // 25 920 millimetre-sized triangles, which a fixed 4e-3 pad would blow up eightfold.

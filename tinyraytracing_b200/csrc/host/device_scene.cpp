@@ -199,8 +199,8 @@ void renderImage(DeviceScene &dev, int spp, double *image, uint64_t seed, int ma
         throw std::runtime_error(std::string("trt_render: ") + trt_last_error());
 }
 
-// triangle.cpp:12-29: least-squares solution of [v0 v1 v2; 1 1 1] b = [p; 1] in double — host copy of the
-// column-pivoted Householder solve the device uses for HitRecord::pn (csrc/barycentric.cuh).
+// triangle.cpp:12-29: least-squares solution of [v0 v1 v2; 1 1 1] b = [p; 1] in double, by the reference's own route
+// (column-pivoted Householder QR).  The device computes the same solution in closed form (csrc/barycentric.cuh).
 vec3 Triangle::findBaryCor(vec3 p)
 {
     double A[4][3] = {{v[0].x, v[1].x, v[2].x}, {v[0].y, v[1].y, v[2].y}, {v[0].z, v[1].z, v[2].z}, {1, 1, 1}};

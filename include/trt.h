@@ -203,6 +203,8 @@ typedef struct trt_layout_report {
     int32_t wide_nodes, wide_depth, ref_leaves, ref_depth, slivers, needles;
     int32_t violations;
     double sah_wide;       /* expected child-box tests per random ray through the root box (surface-area heuristic) */
+    double sah_inner;      /* its part from child boxes that are inner nodes = expected node visits below the root   */
+    double sah_leaf;       /* its part from child boxes that are leaves = expected leaf scans                        */
 } trt_layout_report;
 int trt_layout_check(const trt_scene_desc *desc, trt_layout_report *report);
 

@@ -64,7 +64,8 @@ class Stats(C.Structure):
 class LayoutReport(C.Structure):
     _fields_ = [("n_tris", C.c_int32), ("n_fast_tris", C.c_int32), ("n_dropped", C.c_int32), ("use_wide", C.c_int32),
                 ("wide_nodes", C.c_int32), ("wide_depth", C.c_int32), ("ref_leaves", C.c_int32), ("ref_depth", C.c_int32),
-                ("slivers", C.c_int32), ("needles", C.c_int32), ("violations", C.c_int32), ("sah_wide", C.c_double)]
+                ("slivers", C.c_int32), ("needles", C.c_int32), ("violations", C.c_int32), ("sah_wide", C.c_double),
+                ("sah_inner", C.c_double), ("sah_leaf", C.c_double)]
 
 
 # every symbol include/trt.h and include/trt_host.h declare (tests check the library exports all of them)

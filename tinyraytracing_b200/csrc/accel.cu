@@ -977,6 +977,18 @@ std::string checkLayout(const trt_scene_desc &desc, const AccelBuild &ab, trt_la
         std::vector<Item> todo;
         todo.push_back({0, 1, {-INFINITY, -INFINITY, -INFINITY}, {INFINITY, INFINITY, INFINITY}});
         int maxDepth = 0;
+        // the root's box = union of its children's boxes (the measure buildWide normalises sah_wide with)
+        double rootHalfArea = 1.0;
+        {
+            const WideNode &w = ab.wide_nodes[0];
+            const float *b6[6] = {&w.lox.x, &w.loy.x, &w.loz.x, &w.hix.x, &w.hiy.x, &w.hiz.x};
+            float rlo[3] = {INFINITY, INFINITY, INFINITY}, rhi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (int k = 0; k < 4; ++k)
+                if ((&w.link.x)[k] != TRT_LINK_EMPTY)
+                    for (int a = 0; a < 3; ++a)
+                        rlo[a] = std::fmin(rlo[a], b6[a][k]), rhi[a] = std::fmax(rhi[a], b6[3 + a][k]);
+            rootHalfArea = (double)halfArea(rlo, rhi);
+        }
         while (!todo.empty())
         {
             const Item it = todo.back();
@@ -1009,6 +1021,8 @@ std::string checkLayout(const trt_scene_desc &desc, const AccelBuild &ab, trt_la
                 for (int a = 0; a < 3; ++a)
                     if (!(lo[a] <= hi[a]) || !(lo[a] >= it.lo[a]) || !(hi[a] <= it.hi[a]))
                         bad("child box not finite, inverted, or not inside its parent's box");
+                const double rel = (double)halfArea(lo, hi) / rootHalfArea;
+                (lk[k] < 0 ? rep.sah_leaf : rep.sah_inner) += rel;
                 if (lk[k] < 0)
                     leafInside(lk[k], lo, hi);
                 else

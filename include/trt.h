@@ -208,6 +208,31 @@ typedef struct trt_layout_report {
 } trt_layout_report;
 int trt_layout_check(const trt_scene_desc *desc, trt_layout_report *report);
 
+/* ---- host-only: the GPU layouts as plain arrays (inspection and test tooling, no device needed) ------------------
+   tests/ walks these arrays on the CPU with the traversal rules of DESIGN.md §3 (oracle/layout_walk.cpp, test
+   infrastructure) to check the layout's DATA against the oracle, and tools count node visits per ray class with it.
+   Nothing in the product path reads a trt_layout. */
+typedef struct trt_layout_view {
+    int32_t n_wide_nodes;         /* 0 when the scene is a single scan unit or has no fast layout              */
+    int32_t wide_root;            /* node 0, a leaf link (< 0), or 0x7fffffff = no fast layout                 */
+    int32_t n_fast_tris, n_ref_leaves, n_ref_inner;
+    int32_t check_leaf_box;       /* 0 only when the whole scene is one reference leaf (bvh.cpp:151-154)       */
+    float strict_origin_limit;    /* rays starting farther out take the exhaustive reference walk              */
+    uint32_t miss_key;            /* tie key of the miss state                                    */
+    const float *wide_nodes;      /* n_wide_nodes * 32 words: lox[4] loy[4] loz[4] hix[4] hiy[4] hiz[4] link[4] pad[4] */
+    const float *fast_geom;       /* n_fast_tris * 12: N.xyz p1.xyz p2.xyz p3.xyz                              */
+    const uint32_t *fast_key;     /* n_fast_tris: tie key, higher wins at equal t                              */
+    const int32_t *fast_orig;     /* n_fast_tris: post-build triangle index                                    */
+    const int32_t *fast_leaf;     /* n_fast_tris: reference leaf ordinal                                       */
+    const float *ref_leaf_box;    /* n_ref_leaves * 8: AA.xyz - BB.xyz -                                       */
+    const int32_t *ref_leaf_parent; /* n_ref_leaves: (parent inner index << 1) | right-child bit, -1 = root    */
+    const float *ref_nodes;       /* n_ref_inner * 16 words: left box, right box (6 + 6 floats), left link, right
+                                     link, parent token, unused                                                */
+} trt_layout_view;
+typedef struct trt_layout trt_layout;
+int trt_layout_build(const trt_scene_desc *desc, trt_layout **out, trt_layout_view *view);
+void trt_layout_free(trt_layout *layout);
+
 int trt_get_stats(trt_scene *scene, trt_stats *out);
 int trt_reset_stats(trt_scene *scene);
 const char *trt_last_error(void);

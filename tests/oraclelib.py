@@ -44,6 +44,8 @@ def lib():
         L.orc_uniform.restype = C.c_double
         L.orc_uniform.argtypes = [u64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         L.orc_primary_ray.argtypes = [vp, i32, i32, i32, u64, vp]
+        L.orc_walk_layout.argtypes = [vp, vp, i64, vp, vp, vp, i32]
+        L.orc_walk_layout.restype = None
         _lib = L
     return _lib
 
@@ -161,3 +163,21 @@ def philox(ctr, key):
 
 def uniform(seed, pixel, sample, depth, slot):
     return lib().orc_uniform(seed, pixel, sample, depth, slot)
+
+
+def walk_layout(host_scene, rays, threads=0):
+    """CPU walk (oracle/layout_walk.cpp) of the product's fast layout for `host_scene` (trt_layout_build): returns
+    (ids, t, work) with ids = post-build triangle index, -1 miss, -2 = ray class the fast layout does not serve, and
+    work = per-ray averages of wide nodes visited / child boxes tested / leaves scanned / triangles tested."""
+    rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+    n = len(rays)
+    handle, view = host_scene.layout_arrays()
+    try:
+        ids, t = np.zeros(n, np.int32), np.zeros(n, np.float32)
+        cnt = (C.c_uint64 * 4)(0, 0, 0, 0)
+        lib().orc_walk_layout(C.addressof(view), rays.ctypes.data, n, ids.ctypes.data, t.ctypes.data, C.addressof(cnt), threads)
+    finally:
+        host_scene.free_layout(handle)
+    served = max(int((ids != -2).sum()), 1)
+    work = dict(zip(("nodes", "boxes", "leaves", "tris"), (c / served for c in cnt)))
+    return ids, t, work

@@ -227,3 +227,65 @@ def test_oracle_matches_the_live_reference_including_nan_slabs(name, oracle_scen
     v = host.triangles()["v"]
     hit = oid >= 0
     assert np.array_equal(v[oid[hit]], v[rid[hit]])
+
+
+# ---- the product's fast layout walked on the CPU (oracle/layout_walk.cpp) against the exhaustive reference walk ------
+def _special_rays(host, n, seed):
+    """Zero / denormal direction components, half of the origins exactly on a reference node box plane."""
+    boxes, _ = host.nodes()
+    lo, hi = host.root_box()
+    rng = np.random.default_rng(seed)
+    o = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    axis = rng.integers(0, 3, n)
+    d[np.arange(n), axis] = rng.choice(np.array([0.0, -0.0, 1e-42, -1e-42], np.float32), n)
+    pick, side = rng.integers(0, len(boxes), n), rng.integers(0, 2, n)
+    plane = boxes[pick, axis + 3 * side]
+    on_plane = (rng.random(n) < 0.5) & np.isfinite(plane)
+    o[on_plane, axis[on_plane]] = plane[on_plane]
+    return np.concatenate([o, d], 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("variant", ("default", "no-reinsertion", "optimal-collapse", "leaf-atomic"))
+@pytest.mark.parametrize("name", SCENES)
+def test_fast_layout_walked_on_the_cpu_equals_the_reference_walk(name, variant, oracle_scenes, host_scenes, monkeypatch):
+    """The DATA of the GPU layout (boxes, leaf tags, tie keys, parent links — what trt_scene_create uploads), walked
+    with the rules of DESIGN.md §3 restated on the CPU, gives the reference's triangle ids and distance bits: 100 k
+    config-2 rays plus 40 k rays with zero direction components / origins on box planes per scene, for the default
+    builder and its selectable variants.  No GPU involved; the CUDA kernels are tested against the same oracle."""
+    from conftest import make_rays
+
+    env = {"default": {}, "no-reinsertion": {"TRT_REINSERT": "0"}, "optimal-collapse": {"TRT_COLLAPSE": "optimal"},
+           "leaf-atomic": {"TRT_WIDE_SOURCE": "leaves"}}[variant]
+    for k in ("TRT_REINSERT", "TRT_COLLAPSE", "TRT_WIDE_SOURCE"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    host, orc = host_scenes[name], oracle_scenes[name]
+    rays = np.concatenate([make_rays(host, orc, 100000, seed=41), _special_rays(host, 40000, seed=43)])
+    ids, t, work = oraclelib.walk_layout(host, rays)
+    oid, ot = orc.trace(rays)
+    served = ids != -2
+    assert served.all()  # finite rays from inside the scene: the fast layout serves every one of them
+    assert np.array_equal(ids, oid) and np.array_equal(t.view(np.uint32), ot.view(np.uint32))
+    assert 0 < work["nodes"] < 60 and (oid >= 0).sum() > 30000
+
+
+def test_cpu_walk_counters_are_the_gpu_counters_definition(host_scenes, oracle_scenes):
+    """The walker counts what trt_trace_counters counts (wide nodes visited, child boxes tested, leaves scanned,
+    triangles tested), so builder variants can be compared on real ray populations without a GPU: the optimised tree
+    must not visit more nodes than the plain binned-SAH one on the config-2 population of staircase."""
+    import os
+    from conftest import make_rays
+
+    host, orc = host_scenes["staircase"], oracle_scenes["staircase"]
+    rays = make_rays(host, orc, 60000, seed=47)
+    os.environ.pop("TRT_REINSERT", None)
+    _, _, opt = oraclelib.walk_layout(host, rays)
+    os.environ["TRT_REINSERT"] = "0"
+    try:
+        _, _, plain = oraclelib.walk_layout(host, rays)
+    finally:
+        os.environ.pop("TRT_REINSERT", None)
+    assert opt["nodes"] < plain["nodes"] and opt["boxes"] < plain["boxes"]

@@ -68,10 +68,18 @@ class LayoutReport(C.Structure):
                 ("sah_inner", C.c_double), ("sah_leaf", C.c_double)]
 
 
+class LayoutView(C.Structure):
+    _fields_ = [("n_wide_nodes", C.c_int32), ("wide_root", C.c_int32), ("n_fast_tris", C.c_int32), ("n_ref_leaves", C.c_int32),
+                ("n_ref_inner", C.c_int32), ("check_leaf_box", C.c_int32), ("strict_origin_limit", C.c_float),
+                ("miss_key", C.c_uint32), ("wide_nodes", C.c_void_p), ("fast_geom", C.c_void_p), ("fast_key", C.c_void_p),
+                ("fast_orig", C.c_void_p), ("fast_leaf", C.c_void_p), ("ref_leaf_box", C.c_void_p),
+                ("ref_leaf_parent", C.c_void_p), ("ref_nodes", C.c_void_p)]
+
+
 # every symbol include/trt.h and include/trt_host.h declare (tests check the library exports all of them)
 EXPORTS = ["trt_device_count", "trt_scene_create", "trt_scene_destroy", "trt_host_alloc", "trt_host_free",
            "trt_trace_closest", "trt_trace_closest_async", "trt_trace_counters", "trt_hit_attributes", "trt_render",
-           "trt_render_accumulate", "trt_resolve", "trt_layout_check", "trt_get_stats", "trt_reset_stats", "trt_last_error",
+           "trt_render_accumulate", "trt_resolve", "trt_layout_check", "trt_layout_build", "trt_layout_free", "trt_get_stats", "trt_reset_stats", "trt_last_error",
            "trt_version", "trt_host_scene_load", "trt_host_scene_from_arrays", "trt_host_scene_desc",
            "trt_host_scene_faces", "trt_host_scene_material_name", "trt_host_scene_build_seconds",
            "trt_host_scene_free", "trt_host_scene_save", "trt_host_scene_load_cache", "trt_decode_jpeg", "trt_write_png", "trt_write_pfm"]
@@ -109,6 +117,9 @@ def load_library():
     L.trt_trace_counters.argtypes = [vp, vp, sz, vp]
     L.trt_render.argtypes = [vp, C.POINTER(RenderParams), vp]
     L.trt_layout_check.argtypes = [C.POINTER(SceneDesc), C.POINTER(LayoutReport)]
+    L.trt_layout_build.argtypes = [C.POINTER(SceneDesc), C.POINTER(vp), C.POINTER(LayoutView)]
+    L.trt_layout_free.argtypes = [vp]
+    L.trt_layout_free.restype = None
     L.trt_render_accumulate.argtypes = [vp, C.POINTER(RenderParams), vp, vp]
     L.trt_resolve.argtypes = [vp, vp, i32, vp, vp, vp]
     L.trt_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -174,6 +185,16 @@ class HostScene:
         h = C.c_void_p()
         _check(load_library().trt_host_scene_load_cache(path.encode(), C.byref(h)), "trt_host_scene_load_cache")
         return cls(h)
+
+    def layout_arrays(self):
+        """(handle, LayoutView): the GPU layouts of this scene as plain host arrays (trt_layout_build); release the
+        handle with free_layout().  Inspection / test tooling — the device path never reads it."""
+        h, view = C.c_void_p(), LayoutView()
+        _check(self.lib.trt_layout_build(C.byref(self.desc), C.byref(h), C.byref(view)), "trt_layout_build")
+        return h, view
+
+    def free_layout(self, handle):
+        self.lib.trt_layout_free(handle)
 
     def layout_check(self):
         """Builds the GPU layouts on the host and verifies their invariants (trt_layout_check, no device needed)."""

@@ -533,6 +533,45 @@ int trt_layout_check(const trt_scene_desc *desc, trt_layout_report *report)
     return TRT_OK;
 }
 
+struct trt_layout
+{
+    trt::AccelBuild ab;
+};
+
+int trt_layout_build(const trt_scene_desc *desc, trt_layout **out, trt_layout_view *view)
+{
+    if (!desc || !out || !view)
+        return fail(TRT_ERR_INVALID, "trt_layout_build: null argument");
+    std::unique_ptr<trt_layout> l(new trt_layout());
+    AccelBuild &ab = l->ab;
+    const std::string err = buildAccel(*desc, ab);
+    if (!err.empty())
+        return fail(TRT_ERR_INVALID, "trt_layout_build: " + err);
+    const std::string wide_err = buildWide(*desc, ab);
+    static_assert(sizeof(WideNode) == 128 && sizeof(TriGeom) == 48 && sizeof(RefNode) == 64, "layout records");
+    std::memset(view, 0, sizeof *view);
+    view->n_wide_nodes = (int32_t)ab.wide_nodes.size();
+    view->wide_root = wide_err.empty() ? ab.wide_root : TRT_LINK_EMPTY;
+    view->n_fast_tris = (int32_t)ab.fast_orig.size();
+    view->n_ref_leaves = (int32_t)ab.ref_leaf_parent.size();
+    view->n_ref_inner = (int32_t)ab.ref_nodes.size();
+    view->check_leaf_box = ab.root_is_reference_leaf ? 0 : 1;
+    view->strict_origin_limit = 4.0f * ab.scene_scale;
+    view->miss_key = TRT_MISS_KEY;
+    view->wide_nodes = reinterpret_cast<const float *>(ab.wide_nodes.data());
+    view->fast_geom = reinterpret_cast<const float *>(ab.fast_geom.data());
+    view->fast_key = ab.fast_key.data();
+    view->fast_orig = ab.fast_orig.data();
+    view->fast_leaf = ab.fast_leaf.data();
+    view->ref_leaf_box = reinterpret_cast<const float *>(ab.ref_leaf_box.data());
+    view->ref_leaf_parent = ab.ref_leaf_parent.data();
+    view->ref_nodes = reinterpret_cast<const float *>(ab.ref_nodes.data());
+    *out = l.release();
+    return TRT_OK;
+}
+
+void trt_layout_free(trt_layout *l) { delete l; }
+
 int trt_get_stats(trt_scene *s, trt_stats *out)
 {
     if (!s || !out)

@@ -73,3 +73,19 @@ def test_bench_clock_sampler_degrades_without_a_gpu():
     c.mark()
     out = c.stop()
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(out)
+
+
+def test_headers_compile_as_plain_c(tmp_path):
+    """The boundary is a C ABI: both headers must be valid C99 on their own (no C++ types, no torch types), and every
+    function they declare must be the one the library exports (a declaration/definition mismatch would still link)."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "use.c"
+    src.write_text('#include "trt.h"\n#include "trt_host.h"\n'
+                   "int main(void) { trt_layout_report r; trt_layout_view v; trt_stats s; trt_render_params p;\n"
+                   "  return (int)(sizeof r + sizeof v + sizeof s + sizeof p) == 0; }\n")
+    out = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only",
+                          "-I", os.path.join(root, "include"), str(src)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr

@@ -210,6 +210,8 @@ int trt_scene_create(const trt_scene_desc *desc, int device, trt_scene **out)
         return rc;
     v.check_leaf_box = ab.root_is_reference_leaf ? 0 : 1;
     v.strict_origin_limit = 4.0f * ab.scene_scale;
+    // b * inv and S * inv of the fused culling test stay below 4e30 for every box plane b and admitted origin S
+    v.inv_cull_limit = 1.0e30f / std::max(ab.scene_scale, 1.0f);
 
     std::vector<TriShade> shade(desc->n_tris);
     for (int i = 0; i < desc->n_tris; ++i)

@@ -64,8 +64,11 @@ struct BatchRays
 };
 
 // 9 CTAs per SM (56 registers): the walker is latency-bound, see k_shadow in wavefront.cu
+#ifndef TRT_WALK_CTAS
+#define TRT_WALK_CTAS 9
+#endif
 template <bool POOLED>
-__global__ void __launch_bounds__(kTraceBlock, 9) k_closest_persistent(SceneView sv, const float *__restrict__ rays6, unsigned int n,
+__global__ void __launch_bounds__(kTraceBlock, TRT_WALK_CTAS) k_closest_persistent(SceneView sv, const float *__restrict__ rays6, unsigned int n,
                                                                     int32_t *__restrict__ out_id, float *__restrict__ out_t,
                                                                     unsigned int *counter)
 {

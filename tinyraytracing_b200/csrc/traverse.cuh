@@ -107,6 +107,29 @@ __device__ __forceinline__ bool childPass(float3 S, float3 inv, float ax, float 
     return (t1 >= t0) && (((t0 > 0.0f) ? t0 : t1) > 0.0f);
 }
 
+// Culling test of one of the FAST layout's own child boxes (walkNodeStep / traceWide).  These boxes never decide a
+// hit — a candidate counts only if its reference leaf's box passes childPass above — they only have to contain, with
+// the 256-ulp pad they carry, every point at which a triangle below them can be accepted.  So the test need not be the
+// reference's arithmetic, only conservative within that pad:
+//   * (b - S) * inv is evaluated as fma(b, inv, -(S * inv)): one instruction per plane instead of two.  The result
+//     differs from the exact value by at most 2^-24 |S inv| (the rounding of the precomputed product), i.e. it is the
+//     exact slab distance of an origin moved by half an ulp of |S| <= 4 x scene scale — 1/64 of the pad;
+//   * the far distance is clamped to the best t so far and the near distance to 0, which folds the reference's
+//     "result > 0" rule and the pruning test into one comparison: pass <=> max(t0, 0) <= min(t1, best).  (t1 == 0 with
+//     t0 <= 0 passes here and not in the reference: a superset, harmless for a culling test.)
+// inv is finite here (cullInv clamps it), so no inf - inf can appear; a NaN would be dropped by fminf / fmaxf, which
+// only ever widens the test.  31 -> 18 instructions per child box: the slab tests were 28 % of the walker's issued
+// instructions (profiles/r01_closest_staircase_default.txt).
+__device__ __forceinline__ bool childCull(float3 inv, float3 nsi, float ax, float ay, float az, float bx, float by, float bz,
+                                          float best_t, float &t0c)
+{
+    const float inx = __fmaf_rn(bx, inv.x, nsi.x), iny = __fmaf_rn(by, inv.y, nsi.y), inz = __fmaf_rn(bz, inv.z, nsi.z);
+    const float outx = __fmaf_rn(ax, inv.x, nsi.x), outy = __fmaf_rn(ay, inv.y, nsi.y), outz = __fmaf_rn(az, inv.z, nsi.z);
+    const float t1 = fminf(fminf(fmaxf(inx, outx), fmaxf(iny, outy)), fminf(fmaxf(inz, outz), best_t));
+    t0c = fmaxf(fmaxf(fminf(inx, outx), fminf(iny, outy)), fmaxf(fminf(inz, outz), 0.0f));
+    return t0c <= t1;
+}
+
 // interactBVHNode (bvh.cpp:211-229) over one reference leaf, merged into the running best by (t, key).
 // One fused loop per lane.  Two alternatives were measured on staircase (4 Mi config-2 rays) and rejected:
 // splitting into a plane pass + an inside pass per lane (1.70 vs 2.13 Grays/s: the reloads and the recomputed
@@ -122,8 +145,9 @@ __device__ __forceinline__ bool childPass(float3 S, float3 inv, float ax, float 
 // reciprocal overflows, where "leaf box passes" no longer implies "its ancestors pass".
 // (out of line and with plain pointer arguments: the rare path must not weigh on the register allocation of the walks)
 static __device__ __noinline__ bool refPathPasses(const int32_t *ref_leaf_parent, const RefNode *ref_nodes, int leaf, float3 S,
-                                                  float3 inv)
+                                                  float3 d)
 {
+    const float3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); // the reference's own reciprocal (bvh.cpp:233), +-inf included
     int32_t p = __ldg(ref_leaf_parent + leaf);
     while (p >= 0)
     {
@@ -155,7 +179,7 @@ __device__ __forceinline__ void scanLeaf(const SceneView &sv, int first, int num
         {
             if (FAST && pathGate)
             {
-                if (!refPathPasses(sv.ref_leaf_parent, sv.ref_nodes, __ldg(sv.fast_leaf + i), S, inv))
+                if (!refPathPasses(sv.ref_leaf_parent, sv.ref_nodes, __ldg(sv.fast_leaf + i), S, d))
                     continue;
             }
             else if (FAST && sv.check_leaf_box)
@@ -263,8 +287,10 @@ __device__ __forceinline__ void traceRefTopology(const SceneView &sv, float3 S, 
 __device__ __forceinline__ int rayClass(const SceneView &sv, float3 S, float3 d)
 {
     // 1/d overflows to +-inf for zero AND for denormal components: test the reciprocal itself
+    // (and for components so small that b * inv could overflow in the culling test's fused form, see cullInv)
     const float3 inv = rcpDir(d);
-    const bool inf_rcp = !(fabsf(inv.x) <= 3.4028235e38f) || !(fabsf(inv.y) <= 3.4028235e38f) || !(fabsf(inv.z) <= 3.4028235e38f);
+    const float lim = sv.inv_cull_limit;
+    const bool inf_rcp = !(fabsf(inv.x) <= lim) || !(fabsf(inv.y) <= lim) || !(fabsf(inv.z) <= lim);
     const float sum = ((S.x + S.y) + S.z) + ((d.x + d.y) + d.z); // inf or NaN anywhere -> not finite
     const bool far = fmaxf(fabsf(S.x), fmaxf(fabsf(S.y), fabsf(S.z))) > sv.strict_origin_limit;
     if (far || !(fabsf(sum) < 3.0e38f))
@@ -272,6 +298,17 @@ __device__ __forceinline__ int rayClass(const SceneView &sv, float3 S, float3 d)
     return inf_rcp ? 1 : 0;
 }
 __device__ __forceinline__ bool needsStrictWalk(const SceneView &sv, float3 S, float3 d) { return rayClass(sv, S, d) != 0; }
+
+// Reciprocal direction for the culling tests of a class-1 ray: a component beyond the limit (the ray does not move
+// along that axis within any t <= INF: |d| < 1e-30 x scene scale) is clamped to +-limit, so that fma(b, inv, -S inv)
+// stays finite and keeps the sign of b - S — the slab is passed iff the origin lies inside it, which is what
+// inv = +-inf meant in the un-fused form.  Class-0 rays are below the limit: their culling reciprocal IS 1/d.
+__device__ __forceinline__ float3 cullInv(const SceneView &sv, float3 inv)
+{
+    const float lim = sv.inv_cull_limit;
+    return f3(copysignf(fminf(fabsf(inv.x), lim), inv.x), copysignf(fminf(fabsf(inv.y), lim), inv.y),
+              copysignf(fminf(fabsf(inv.z), lim), inv.z));
+}
 
 // A 128-byte wide node in four 256-bit loads (LDG.E.256, sm_100) instead of seven 128-bit ones: with every lane on
 // a different node the L1 data pipe pays one wavefront per lane per load instruction, and ncu shows that pipe at 73 %
@@ -310,16 +347,56 @@ struct TraceCounters
     uint32_t nodes, boxes, leaves, tris;
 };
 
+// One visit of a 4-wide node: culling tests of the (up to) four children, the passing ones sorted by entry distance
+// (5-comparator network; misses sort to the end).  On return nh = number of passing children, (k0,l0) the nearest,
+// (k1,l1) .. (k3,l3) the others near-to-far.  Shared by the plain and the persistent walk.
+struct NodeOrder
+{
+    float k0, k1, k2, k3;
+    int32_t l0, l1, l2, l3;
+    int nh;
+};
+__device__ __forceinline__ NodeOrder visitWideNode(const WideNode *node, float3 inv, float3 nsi, float best_t)
+{
+    const NodeRegs nr = loadWideNode(node);
+    const float4 lox = nr.lox, loy = nr.loy, loz = nr.loz, hix = nr.hix, hiy = nr.hiy, hiz = nr.hiz;
+    const int4 lk = nr.lk;
+    float t0, t1, t2, t3;
+    const bool h0 = childCull(inv, nsi, lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, best_t, t0);
+    const bool h1 = childCull(inv, nsi, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, best_t, t1);
+    const bool h2 = (lk.z != TRT_LINK_EMPTY) && childCull(inv, nsi, lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, best_t, t2);
+    const bool h3 = (lk.w != TRT_LINK_EMPTY) && childCull(inv, nsi, lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, best_t, t3);
+    NodeOrder o;
+    o.k0 = h0 ? t0 : 3.0e38f, o.k1 = h1 ? t1 : 3.0e38f, o.k2 = h2 ? t2 : 3.0e38f, o.k3 = h3 ? t3 : 3.0e38f;
+    o.l0 = lk.x, o.l1 = lk.y, o.l2 = lk.z, o.l3 = lk.w;
+#define TRT_CSWAP(ka, la, kb, lb)                                                                                   \
+    {                                                                                                               \
+        const bool sw = kb < ka;                                                                                    \
+        const float tk = sw ? kb : ka;                                                                              \
+        const int32_t tl = sw ? lb : la;                                                                            \
+        kb = sw ? ka : kb, lb = sw ? la : lb, ka = tk, la = tl;                                                     \
+    }
+    TRT_CSWAP(o.k0, o.l0, o.k1, o.l1)
+    TRT_CSWAP(o.k2, o.l2, o.k3, o.l3)
+    TRT_CSWAP(o.k0, o.l0, o.k2, o.l2)
+    TRT_CSWAP(o.k1, o.l1, o.k3, o.l3)
+    TRT_CSWAP(o.k1, o.l1, o.k2, o.l2)
+#undef TRT_CSWAP
+    o.nh = (int)h0 + (int)h1 + (int)h2 + (int)h3;
+    return o;
+}
+
 // 4-wide walk of the fast layout: while-while (inner nodes until a leaf is reached, then the leaf scan),
-// nearest child first, entry-distance pruning at push and at pop.
+// nearest child first, entry-distance pruning at push and at pop.  cls = rayClass (0 or 1).
 template <bool STATS>
-__device__ __forceinline__ void traceWide(const SceneView &sv, float3 S, float3 d, Hit &hit, TraceCounters *cnt,
-                                          bool pathGate = false)
+__device__ __forceinline__ void traceWide(const SceneView &sv, float3 S, float3 d, Hit &hit, TraceCounters *cnt, int cls = 0)
 {
     hit.t = TRT_INF, hit.id = -1, hit.key = 0xFFFFFFFFu;
     if (sv.wide_root == TRT_LINK_EMPTY)
         return;
     const float3 inv = rcpDir(d);
+    const float3 cinv = (cls == 1) ? cullInv(sv, inv) : inv;
+    const float3 nsi = f3(-(S.x * cinv.x), -(S.y * cinv.y), -(S.z * cinv.z));
     StackEntry stack[TRT_WIDE_STACK];
     stack[0] = packEntry(-1.f, TRT_LINK_EXIT);
     int sp = 1;
@@ -328,39 +405,13 @@ __device__ __forceinline__ void traceWide(const SceneView &sv, float3 S, float3 
     {
         while (cur >= 0)
         {
-            const NodeRegs nr = loadWideNode(sv.wide_nodes + cur);
-            const float4 lox = nr.lox, loy = nr.loy, loz = nr.loz, hix = nr.hix, hiy = nr.hiy, hiz = nr.hiz;
-            const int4 lk = nr.lk;
-            float t0, t1, t2, t3;
-            bool h0 = childPass(S, inv, lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, t0);
-            bool h1 = childPass(S, inv, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, t1);
-            bool h2 = (lk.z != TRT_LINK_EMPTY) && childPass(S, inv, lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, t2);
-            bool h3 = (lk.w != TRT_LINK_EMPTY) && childPass(S, inv, lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, t3);
+            const NodeOrder o = visitWideNode(sv.wide_nodes + cur, cinv, nsi, hit.t);
             if (STATS)
+            {
+                const int4 lk = __ldg(&sv.wide_nodes[cur].link);
                 cnt->nodes++, cnt->boxes += 2 + (lk.z != TRT_LINK_EMPTY) + (lk.w != TRT_LINK_EMPTY);
-            h0 = h0 && !(t0 > hit.t);
-            h1 = h1 && !(t1 > hit.t);
-            h2 = h2 && !(t2 > hit.t);
-            h3 = h3 && !(t3 > hit.t);
-            // order the hit children by entry distance (5-comparator network; misses sort to the end), continue
-            // with the nearest and push the rest far-to-near so that they pop near-to-far
-            float k0 = h0 ? t0 : 3.0e38f, k1 = h1 ? t1 : 3.0e38f, k2 = h2 ? t2 : 3.0e38f, k3 = h3 ? t3 : 3.0e38f;
-            int32_t l0 = lk.x, l1 = lk.y, l2 = lk.z, l3 = lk.w;
-#define TRT_CSWAP(ka, la, kb, lb)                                                                                   \
-    {                                                                                                               \
-        const bool sw = kb < ka;                                                                                    \
-        const float tk = sw ? kb : ka;                                                                              \
-        const int32_t tl = sw ? lb : la;                                                                            \
-        kb = sw ? ka : kb, lb = sw ? la : lb, ka = tk, la = tl;                                                     \
-    }
-            TRT_CSWAP(k0, l0, k1, l1)
-            TRT_CSWAP(k2, l2, k3, l3)
-            TRT_CSWAP(k0, l0, k2, l2)
-            TRT_CSWAP(k1, l1, k3, l3)
-            TRT_CSWAP(k1, l1, k2, l2)
-#undef TRT_CSWAP
-            const int nh = (int)h0 + (int)h1 + (int)h2 + (int)h3;
-            if (nh == 0)
+            }
+            if (o.nh == 0)
             {
                 StackEntry e;
                 do
@@ -370,14 +421,13 @@ __device__ __forceinline__ void traceWide(const SceneView &sv, float3 S, float3 
                 cur = entryLink(e);
                 continue;
             }
-            if (nh > 3)
-                stack[sp++] = packEntry(k3, l3);
-            if (nh > 2)
-                stack[sp++] = packEntry(k2, l2);
-            if (nh > 1)
-                stack[sp++] = packEntry(k1, l1);
-            const int32_t next = l0;
-            cur = next;
+            if (o.nh > 3)
+                stack[sp++] = packEntry(o.k3, o.l3);
+            if (o.nh > 2)
+                stack[sp++] = packEntry(o.k2, o.l2);
+            if (o.nh > 1)
+                stack[sp++] = packEntry(o.k1, o.l1);
+            cur = o.l0;
         }
         if (cur == TRT_LINK_EXIT)
         {
@@ -387,7 +437,7 @@ __device__ __forceinline__ void traceWide(const SceneView &sv, float3 S, float3 
         const int leaf = ~cur;
         if (STATS)
             cnt->leaves++, cnt->tris += (leaf & 7) + 1;
-        scanLeaf<true>(sv, leaf >> 3, (leaf & 7) + 1, S, d, inv, hit, pathGate);
+        scanLeaf<true>(sv, leaf >> 3, (leaf & 7) + 1, S, d, inv, hit, cls == 1);
         StackEntry e;
         do
         {
@@ -403,11 +453,13 @@ __device__ __forceinline__ void traceWide(const SceneView &sv, float3 S, float3 
 //   * lanes fetch a new ray from a global counter as soon as enough lanes of the warp are idle (no tail);
 //   * the inner-node loop and the leaf loop are warp-uniform: a lane that reaches a leaf postpones it and keeps
 //     walking inner nodes until no lane of the warp still lacks a leaf, then the warp scans leaves together.
+//     (Putting the next phase to a vote each step — the one with more lanes ready wins — was measured in round 2:
+//     two more ballots per step cost more than the stragglers it removes, staircase 6.44 -> 5.96 Grays/s.)
 // Results are identical to traceWide: only the order in which a ray's own nodes are visited changes, and the
 // (t, key) order decides the winner (see the header comment).
 struct WalkState
 {
-    float3 S, d, inv;
+    float3 S, d, inv, nsi; // inv: 1/d (the culling reciprocal of a class-1 ray, see cullInv); nsi = -(S * inv)
     Hit hit;
     int32_t cur, leaf; // cur: inner node / leaf link / TRT_LINK_EXIT; leaf: postponed leaf link or TRT_LINK_EMPTY
     int sp;
@@ -427,49 +479,25 @@ struct WalkState
 // One inner-node step of lane state `st` (st.cur >= 0 on entry).
 __device__ __forceinline__ void walkNodeStep(const SceneView &sv, WalkState &st, StackEntry *stack)
 {
-    const NodeRegs nr = loadWideNode(sv.wide_nodes + st.cur);
-    const float4 lox = nr.lox, loy = nr.loy, loz = nr.loz, hix = nr.hix, hiy = nr.hiy, hiz = nr.hiz;
-    const int4 lk = nr.lk;
-    float t0, t1, t2, t3;
-    bool h0 = childPass(st.S, st.inv, lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, t0);
-    bool h1 = childPass(st.S, st.inv, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, t1);
-    bool h2 = (lk.z != TRT_LINK_EMPTY) && childPass(st.S, st.inv, lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, t2);
-    bool h3 = (lk.w != TRT_LINK_EMPTY) && childPass(st.S, st.inv, lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, t3);
-    h0 = h0 && !(t0 > st.hit.t);
-    h1 = h1 && !(t1 > st.hit.t);
-    h2 = h2 && !(t2 > st.hit.t);
-    h3 = h3 && !(t3 > st.hit.t);
-    float k0 = h0 ? t0 : 3.0e38f, k1 = h1 ? t1 : 3.0e38f, k2 = h2 ? t2 : 3.0e38f, k3 = h3 ? t3 : 3.0e38f;
-    int32_t l0 = lk.x, l1 = lk.y, l2 = lk.z, l3 = lk.w;
-#define TRT_CSWAP(ka, la, kb, lb)                                                                                   \
-    {                                                                                                               \
-        const bool sw = kb < ka;                                                                                    \
-        const float tk = sw ? kb : ka;                                                                              \
-        const int32_t tl = sw ? lb : la;                                                                            \
-        kb = sw ? ka : kb, lb = sw ? la : lb, ka = tk, la = tl;                                                     \
-    }
-    TRT_CSWAP(k0, l0, k1, l1)
-    TRT_CSWAP(k2, l2, k3, l3)
-    TRT_CSWAP(k0, l0, k2, l2)
-    TRT_CSWAP(k1, l1, k3, l3)
-    TRT_CSWAP(k1, l1, k2, l2)
-#undef TRT_CSWAP
-    const int nh = (int)h0 + (int)h1 + (int)h2 + (int)h3;
-    if (nh == 0)
+    const NodeOrder o = visitWideNode(sv.wide_nodes + st.cur, st.inv, st.nsi, st.hit.t);
+    if (o.nh == 0)
     {
         TRT_WALK_POP(st, stack);
         return;
     }
-    if (nh > 3)
-        stack[st.sp++] = packEntry(k3, l3);
-    if (nh > 2)
-        stack[st.sp++] = packEntry(k2, l2);
-    if (nh > 1)
-        stack[st.sp++] = packEntry(k1, l1);
-    st.cur = l0;
+    if (o.nh > 3)
+        stack[st.sp++] = packEntry(o.k3, o.l3);
+    if (o.nh > 2)
+        stack[st.sp++] = packEntry(o.k2, o.l2);
+    if (o.nh > 1)
+        stack[st.sp++] = packEntry(o.k1, o.l1);
+    st.cur = o.l0;
 }
 
 #define TRT_WALK_WARPS 4 // warps per CTA of every kernel that calls walkPersistent (128 threads)
+#ifndef TRT_WALK_REFILL
+#define TRT_WALK_REFILL 8 // refill once this many lanes of the warp are idle
+#endif
 
 // Inside tests of n (<= 32) pooled candidates, one per lane; the ray comes from the owner lane's registers.
 __device__ __forceinline__ void walkPoolInside(const SceneView &sv, const WalkState &st, const int32_t *pool_tri,
@@ -500,19 +528,19 @@ __device__ __forceinline__ void walkPoolInside(const SceneView &sv, const WalkSt
 }
 
 // RAYS: struct with  unsigned locate(unsigned i)  (ray index -> the 32-bit token the walker keeps while the ray is in
-// flight, never 0xffffffff),  void load(token, float3 &S, float3 &d),  void store(token, const Hit &)  (hit.id = post-build
+// flight, below 2^31),  void load(token, float3 &S, float3 &d),  void store(token, const Hit &)  (hit.id = post-build
 // triangle index)  and  void storeFast(sv, token, const Hit &)  (hit.id = index in the fast layout's own order).
 // `counter` must be zero at launch; n = number of rays.  Every thread of the block must call this.
 // POOLED selects the leaf phase: false = every lane scans its own leaf (scanLeaf); true = the warp pools the
 // candidates that pass the plane test and deals their inside tests out one per lane (see below; measured in
 // profiles/r01_closest_staircase_leaflayout_pooled.txt: 8 % fewer instructions at 15 instead of 9.5 lanes, but the shorter
 // dependent chains expose L1 latency — 69 % instead of 83 % issue-active — and it is 9 % slower, so it is off
-// by default and kept selectable (TRT_TRACE_POOLED) for the next round's latency work).
+// by default and kept selectable (TRT_TRACE_POOLED)).
 template <bool POOLED, typename RAYS>
 __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, unsigned int n, unsigned int *counter)
 {
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int kRefillIdle = 8; // refill once this many lanes of the warp are idle
+    constexpr int kRefillIdle = TRT_WALK_REFILL;
     constexpr unsigned kPathGateBit = 0x80000000u;
     const int lane = threadIdx.x & 31;
     // per warp: pool of (triangle, t, owner lane) candidates awaiting their inside test, and each lane's best
@@ -528,6 +556,7 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
     unsigned long long *best = s_best[warp];
     StackEntry stack[TRT_WIDE_STACK];
     WalkState st;
+    st.cur = TRT_LINK_EXIT, st.leaf = TRT_LINK_EMPTY, st.sp = 1;
     unsigned int ray = 0xffffffffu; // idle
     bool drained = false;           // the pool is empty
     for (;;)
@@ -566,9 +595,13 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                     {
                         if (POOLED)
                             best[lane] = ((unsigned long long)__float_as_uint(TRT_INF) << 32) | sv.miss_rank;
-                        if (cls == 1)
-                            ray |= kPathGateBit; // tokens stay below 2^31: the top bit marks a class-1 ray (rayClass)
                         st.inv = rcpDir(st.d);
+                        if (cls == 1)
+                        {
+                            ray |= kPathGateBit; // tokens stay below 2^31: the top bit marks a class-1 ray (rayClass)
+                            st.inv = cullInv(sv, st.inv);
+                        }
+                        st.nsi = f3(-(st.S.x * st.inv.x), -(st.S.y * st.inv.y), -(st.S.z * st.inv.z));
                         stack[0] = packEntry(-1.f, TRT_LINK_EXIT);
                         st.sp = 1;
                         st.cur = sv.wide_root;
@@ -698,6 +731,6 @@ __device__ __forceinline__ void traceClosest(const SceneView &sv, float3 S, floa
     else if (cls == 2)
         traceRefTopology<true>(sv, S, d, hit);
     else
-        traceWide<false>(sv, S, d, hit, nullptr, cls == 1);
+        traceWide<false>(sv, S, d, hit, nullptr, cls);
 }
 } // namespace trt

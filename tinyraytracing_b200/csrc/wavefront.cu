@@ -2,14 +2,20 @@
 // as a sequence of kernels over a batch of paths held in HBM (SoA), one iteration per path depth:
 //
 //   k_raygen      (K1)  main.cpp:88-95 + Camera::getRay           -> ray[slot], queue = all slots
-//   k_trace       (K2)  traverseBVH for the queue                  -> hit[slot]
-//   k_shade       (K3)  shade(): emissive return, Kd/texture, per-light NEE sample (emits "shadow" rays),
-//                       RR, nextRay/Sample -> next ray, throughput weight, next queue (warp-aggregated append)
-//   k_shadow      (K4)  pathTracing.cpp:51-58: closest hit of the light sample ray; the sample counts only if
-//                       the CLOSEST hit's material is the light's material (not an any-hit test)
-//   k_accumulate  (K5)  L[slot] += throughput * sum(visible light samples, XML order); throughput *= weight
-//   k_deposit           after the batch: accum[pixel] += sum over the batch's samples of L (double, fixed order)
-//   k_resolve     (K6)  accum / spp (main.cpp:101) and the gamma-2.2 8-bit pack of imshow (main.cpp:30-38)
+//   k_walk        (K2)  ONE persistent walker launch per depth over two kinds of rays: traverseBVH for the queue's
+//                       paths -> hit[slot], and pathTracing.cpp:51-58 for the light-sample ("shadow") rays the
+//                       previous depth's k_shade emitted: closest hit, the sample counts only if the CLOSEST hit's
+//                       material is the light's material (not an any-hit test)
+//   k_shade       (K3)  first settles the path's previous vertex — L[slot] += throughput * sum(visible light samples,
+//                       XML order); throughput *= weight — then shade(): emissive return, Kd/texture, per-light NEE
+//                       sample (emits shadow rays), RR, nextRay/Sample -> next ray, weight, next queue
+//   k_deposit           after the batch: settles the last vertex of every path the same way, then
+//                       accum[pixel] += sum over the batch's samples of L (double, fixed order)
+//   k_resolve     (K4)  accum / spp (main.cpp:101) and the gamma-2.2 8-bit pack of imshow (main.cpp:30-38)
+//
+// Two launches per depth (round 1 had five: trace, counter reset, shade, shadow, accumulate).  A 512x512 16-spp job is
+// 42 depths of ever fewer paths, each launch at least one wave and a launch gap whatever the queue length, so the
+// launches per depth set its time.
 //
 // A path's slot = (sample_in_batch * W*H + pixel): pixel / sample never need storing, each pixel-sample is
 // owned by exactly one slot, so there are no floating-point atomics and the image is bit-reproducible for a
@@ -22,6 +28,7 @@
 #include "barycentric.cuh"
 
 #include <algorithm>
+#include <memory>
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -70,12 +77,15 @@ struct WfBuffers
     int32_t *queue[2];
     float4 *sh_o, *sh_d; // sh_o.w = contribution index (slot*n_lights + light), sh_d.w = light material
     float4 *sh_contrib;  // [slot*n_lights + light]
-    // [0],[1]: path queue sizes (ping-pong); [2],[3]: ray-pool cursors of the persistent trace / shadow kernels;
-    // [kShadowCount + l]: shadow rays queued for light l (segment l of sh_o / sh_d starts at l * capacity)
+    // [0],[1]: path queue sizes (ping-pong); [kPool]: ray-pool cursor of the persistent walker; [kDone]: CTAs of the
+    // running k_walk that have finished; [kShadowCount + l]: shadow rays queued for light l (segment l of sh_o / sh_d
+    // starts at l * capacity)
     int32_t *counters;
     int32_t capacity; // paths per batch = length of one per-light shadow segment
 };
-constexpr int kPoolTrace = 2, kPoolShadow = 3, kShadowCount = 8, kNumCounters = 8 + 32;
+constexpr int kPool = 2, kDone = 3, kShadowCount = 8, kNumCounters = 8 + 32;
+// walker tokens: bit 31 is the walker's own class-1 mark, bit 30 tells a shadow-queue entry from a path slot
+constexpr unsigned kShadowBit = 0x40000000u;
 
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
                                               uint32_t out[4])
@@ -126,6 +136,8 @@ __device__ __forceinline__ float4 xyzw(float3 v, float w) { return make_float4(v
 __global__ void __launch_bounds__(kBlock) k_raygen(SceneView sv, WfBuffers wf, int n_paths, int sample0, uint64_t seed)
 {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0 && threadIdx.x < kNumCounters) // queue 0 = every slot; empty next queue, shadow segments, cursors
+        wf.counters[threadIdx.x] = (threadIdx.x == 0) ? n_paths : 0;
     if (slot >= n_paths)
         return;
     const int W = sv.cam.width, H = sv.cam.height, npix = W * H;
@@ -146,46 +158,25 @@ __global__ void __launch_bounds__(kBlock) k_raygen(SceneView sv, WfBuffers wf, i
     wf.ray_d[slot] = xyzw(d, __int_as_float(CAMERA));
     wf.thr[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
     wf.L[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    wf.nee_mask[slot] = 0u; // no vertex to settle yet
     wf.queue[0][slot] = slot;
-    if (slot == 0)
-    {
-        wf.counters[0] = n_paths;
-        wf.counters[1] = 0;
-        wf.counters[kPoolTrace] = 0;
-    }
 }
 
-// ------------------------------------------------------------------------------------------------ K2 / K4
-struct QueueRays // closest-hit rays of the live paths; token = path slot
-{
-    WfBuffers wf;
-    int qsel;
-    __device__ __forceinline__ unsigned int locate(unsigned int i) const { return (unsigned int)wf.queue[qsel][i]; }
-    __device__ __forceinline__ void load(unsigned int slot, float3 &S, float3 &d) const
-    {
-        S = xyz(wf.ray_o[slot]), d = xyz(wf.ray_d[slot]);
-    }
-    __device__ __forceinline__ void store(unsigned int slot, const Hit &h) const
-    {
-        wf.hit_id[slot] = h.id;
-        wf.hit_t[slot] = h.t;
-    }
-    __device__ __forceinline__ void storeFast(const SceneView &sv, unsigned int slot, Hit h) const
-    {
-        h.id = (h.id >= 0) ? __ldg(sv.fast_orig + h.id) : -1; // fast index -> post-build index
-        store(slot, h);
-    }
-};
-
-// light-sample rays, one queue segment per light (neighbouring lanes: same light, nearby pixels); token = entry index
-// in sh_o / sh_d (light * capacity + position, below 2^31 by the batch-size check of renderAccumulate)
-struct ShadowRays
+// ------------------------------------------------------------------------------------------------ K2
+// The walker's ray pool of one depth: first the closest-hit rays of the live paths (token = path slot), then the
+// light-sample rays, one queue segment per light (neighbouring lanes: same light, nearby pixels; token = kShadowBit |
+// entry index in sh_o / sh_d = light * capacity + position; both below 2^30 by the batch-size check of renderAccumulate).
+struct WalkRays
 {
     WfBuffers wf;
     const TriShade *tri_shade;
-    int n_lights;
+    int n_lights, qsel;
+    unsigned int n_closest;
     __device__ __forceinline__ unsigned int locate(unsigned int i) const
     {
+        if (i < n_closest)
+            return (unsigned int)wf.queue[qsel][i];
+        i -= n_closest;
         int l = 0;
         for (; l < n_lights - 1; ++l)
         {
@@ -194,26 +185,35 @@ struct ShadowRays
                 break;
             i -= c;
         }
-        return (unsigned int)l * (unsigned int)wf.capacity + i;
+        return kShadowBit | ((unsigned int)l * (unsigned int)wf.capacity + i);
     }
-    __device__ __forceinline__ void load(unsigned int e, float3 &S, float3 &d) const
+    __device__ __forceinline__ void load(unsigned int tok, float3 &S, float3 &d) const
     {
-        S = xyz(wf.sh_o[e]), d = xyz(wf.sh_d[e]);
+        const bool sh = (tok & kShadowBit) != 0;
+        const unsigned int e = tok & ~kShadowBit;
+        const float4 o = sh ? wf.sh_o[e] : wf.ray_o[e], dd = sh ? wf.sh_d[e] : wf.ray_d[e];
+        S = xyz(o), d = xyz(dd);
     }
     // pathTracing.cpp:54-58: visible iff the closest hit's material is the light's material
-    __device__ __forceinline__ void finish(unsigned int e, bool hit, int mtl) const
+    __device__ __forceinline__ void finishShadow(unsigned int e, bool hit, int mtl) const
     {
         const bool visible = hit && mtl == __float_as_int(wf.sh_d[e].w);
         if (!visible)
             wf.sh_contrib[__float_as_int(wf.sh_o[e].w)] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __device__ __forceinline__ void store(unsigned int e, const Hit &h) const
+    __device__ __forceinline__ void store(unsigned int tok, const Hit &h) const
     {
-        finish(e, h.id >= 0, h.id >= 0 ? tri_shade[h.id].mtl : -1);
+        if (tok & kShadowBit)
+            finishShadow(tok & ~kShadowBit, h.id >= 0, h.id >= 0 ? tri_shade[h.id].mtl : -1);
+        else
+            wf.hit_id[tok] = h.id, wf.hit_t[tok] = h.t;
     }
-    __device__ __forceinline__ void storeFast(const SceneView &sv, unsigned int e, const Hit &h) const
+    __device__ __forceinline__ void storeFast(const SceneView &sv, unsigned int tok, const Hit &h) const
     {
-        finish(e, h.id >= 0, h.id >= 0 ? __ldg(sv.fast_mtl + h.id) : -1); // one load from a dense 4-byte table
+        if (tok & kShadowBit) // a light sample needs only the hit's material: one load from a dense 4-byte table
+            finishShadow(tok & ~kShadowBit, h.id >= 0, h.id >= 0 ? __ldg(sv.fast_mtl + h.id) : -1);
+        else
+            wf.hit_id[tok] = (h.id >= 0) ? __ldg(sv.fast_orig + h.id) : -1, wf.hit_t[tok] = h.t; // fast -> post-build index
     }
 };
 
@@ -235,31 +235,48 @@ __device__ __forceinline__ void traceGridStride(const SceneView &sv, RAYS &rays,
     }
 }
 
+// what: bit 0 = the queue's closest-hit rays, bit 1 = the shadow rays, bit 2 = this is the depth's last walk: the CTA
+// that finishes last zeroes the counters k_shade is about to fill (next queue size, shadow segments).  The pool cursor
+// is zeroed by every launch's last CTA.  (TRT_RENDER_PROFILE walks the two kinds in two launches to time them apart.)
+// 9 resident CTAs per SM = 56 registers instead of 64 / 8 CTAs: the walker is latency-bound (ncu: 1.4 eligible warps
+// per cycle), one more CTA of warps pays; 10 CTAs = 48 registers spill 134 bytes and lose.
+#ifndef TRT_WALK_CTAS
+#define TRT_WALK_CTAS 9
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_trace(SceneView sv, WfBuffers wf, int qsel)
+__global__ void __launch_bounds__(kBlock, TRT_WALK_CTAS) k_walk(SceneView sv, WfBuffers wf, int qsel, int what)
 {
-    QueueRays r{wf, qsel};
-    const unsigned int n = (unsigned int)wf.counters[qsel];
+    unsigned int n_sh = 0;
+    if (what & 2)
+        for (int l = 0; l < sv.n_lights; ++l)
+            n_sh += (unsigned int)wf.counters[kShadowCount + l];
+    WalkRays r{wf, sv.tri_shade, sv.n_lights, qsel, (what & 1) ? (unsigned int)wf.counters[qsel] : 0u};
+    const unsigned int n = r.n_closest + n_sh;
     if (MODE != 0)
         traceGridStride<MODE>(sv, r, n);
     else
-        walkPersistent<false>(sv, r, n, reinterpret_cast<unsigned int *>(wf.counters + kPoolTrace));
-}
-
-// 9 resident CTAs per SM = 56 registers (24 bytes of spills) instead of 64 / 8 CTAs: the walker is latency-bound (ncu:
-// 1.4 eligible warps per cycle), one more CTA of warps pays (staircase 72.1 -> 70.8 ms of k_shadow, veach-mis 32.6 -> 32.2);
-// 10 CTAs = 48 registers spill 134 bytes and lose (83.6 ms).  k_trace needs 56 registers as it is.
-template <int MODE>
-__global__ void __launch_bounds__(kBlock, 9) k_shadow(SceneView sv, WfBuffers wf)
-{
-    ShadowRays r{wf, sv.tri_shade, sv.n_lights};
-    unsigned int n = 0;
-    for (int l = 0; l < sv.n_lights; ++l)
-        n += (unsigned int)wf.counters[kShadowCount + l];
-    if (MODE != 0)
-        traceGridStride<MODE>(sv, r, n);
-    else
-        walkPersistent<false>(sv, r, n, reinterpret_cast<unsigned int *>(wf.counters + kPoolShadow));
+        walkPersistent<false>(sv, r, n, reinterpret_cast<unsigned int *>(wf.counters + kPool));
+    // every CTA has read the counters before it got here; the last one to arrive resets them for what follows
+    __syncthreads();
+    __shared__ bool s_last;
+    if (threadIdx.x == 0)
+    {
+        __threadfence();
+        s_last = atomicAdd(reinterpret_cast<unsigned int *>(wf.counters + kDone), 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last)
+    {
+        if (threadIdx.x == 0)
+            wf.counters[kPool] = 0, wf.counters[kDone] = 0;
+        if (what & 4)
+        {
+            if (threadIdx.x == 0)
+                wf.counters[qsel ^ 1] = 0;
+            if (threadIdx.x < 32)
+                wf.counters[kShadowCount + threadIdx.x] = 0;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ K3
@@ -302,6 +319,22 @@ __device__ __forceinline__ void appendQueue(int32_t *counter, int32_t *queue, bo
         queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
 }
 
+// Settles the vertex a path was shaded at last: the light samples whose shadow ray found the light are added in XML
+// order (L_dir += ..., pathTracing.cpp:70) and weighted by the throughput up to that vertex.  Round 1 did this in a
+// kernel of its own after the shadow kernel; now the path's NEXT k_shade (or k_deposit, for a path that ended) does it,
+// with the same operations in the same order per path.
+__device__ __forceinline__ void settleVertex(const WfBuffers &wf, int n_lights, int slot, uint32_t mask, float4 T, float4 &L)
+{
+    float3 Ldir = f3(0.f, 0.f, 0.f);
+    while (mask)
+    {
+        const int li = __ffs(mask) - 1;
+        mask &= mask - 1;
+        Ldir = Ldir + xyz(wf.sh_contrib[slot * n_lights + li]);
+    }
+    L.x += T.x * Ldir.x, L.y += T.y * Ldir.y, L.z += T.z * Ldir.z;
+}
+
 __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) k_shade(SceneView sv, WfBuffers wf, int qsel, int depth, int max_depth,
                                                   int sample0, uint64_t seed)
 {
@@ -321,6 +354,22 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) k_shade(SceneVie
         const int tri = wf.hit_id[slot];
         const float4 rd4 = wf.ray_d[slot];
         const int via = __float_as_int(rd4.w);
+        if (depth > 0)
+        {
+            // the previous vertex: its light samples (their shadow rays were walked together with this path's ray),
+            // then throughput *= weight of the bounce that led here (:84-98)
+            float4 T = wf.thr[slot];
+            const uint32_t pm = wf.nee_mask[slot];
+            if (pm)
+            {
+                float4 L = wf.L[slot];
+                settleVertex(wf, sv.n_lights, slot, pm, T, L);
+                wf.L[slot] = L;
+            }
+            const float4 w = wf.weight[slot];
+            T.x *= w.x, T.y *= w.y, T.z *= w.z;
+            wf.thr[slot] = T;
+        }
         if (tri >= 0)
         {
             const TriShade ts = sv.tri_shade[tri];
@@ -524,44 +573,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) k_shade(SceneVie
   }
 }
 
-// ------------------------------------------------------------------------------------------------ K5
-__global__ void __launch_bounds__(kBlock) k_accumulate(SceneView sv, WfBuffers wf, int qsel)
-{
-  const int count = wf.counters[qsel];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
-  {
-    const int slot = wf.queue[qsel][i];
-    uint32_t mask = wf.nee_mask[slot];
-    float4 T = wf.thr[slot];
-    if (mask)
-    {
-        float3 Ldir = f3(0.f, 0.f, 0.f);
-        while (mask)
-        {
-            const int li = __ffs(mask) - 1;
-            mask &= mask - 1;
-            Ldir = Ldir + xyz(wf.sh_contrib[slot * sv.n_lights + li]); // L_dir += ..., lights in XML order (:70)
-        }
-        float4 L = wf.L[slot];
-        L.x += T.x * Ldir.x, L.y += T.y * Ldir.y, L.z += T.z * Ldir.z;
-        wf.L[slot] = L;
-    }
-    const float4 w = wf.weight[slot];
-    T.x *= w.x, T.y *= w.y, T.z *= w.z;
-    wf.thr[slot] = T;
-  }
-}
-
-__global__ void k_reset_counters(WfBuffers wf, int qnext)
-{
-    // before k_shade of an iteration: the queue it fills, the shadow segments and the ray-pool cursors start at 0
-    if (threadIdx.x == 0)
-        wf.counters[qnext] = 0, wf.counters[kPoolTrace] = 0, wf.counters[kPoolShadow] = 0;
-    if (threadIdx.x < 32)
-        wf.counters[kShadowCount + threadIdx.x] = 0;
-}
-
-__global__ void __launch_bounds__(256) k_deposit(WfBuffers wf, double *accum, int npix, int samples_in_batch)
+__global__ void __launch_bounds__(256) k_deposit(WfBuffers wf, double *accum, int npix, int samples_in_batch, int n_lights)
 {
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= npix)
@@ -569,7 +581,11 @@ __global__ void __launch_bounds__(256) k_deposit(WfBuffers wf, double *accum, in
     double r = 0, g = 0, b = 0;
     for (int s = 0; s < samples_in_batch; ++s)
     {
-        const float4 L = wf.L[(size_t)s * npix + pix];
+        const int slot = s * npix + pix;
+        float4 L = wf.L[slot];
+        const uint32_t pm = wf.nee_mask[slot]; // a path that ended after a vertex with light samples: settle it
+        if (pm)
+            settleVertex(wf, n_lights, slot, pm, wf.thr[slot], L);
         r += (double)L.x, g += (double)L.y, b += (double)L.z;
     }
     accum[(size_t)pix * 3 + 0] += r;
@@ -606,37 +622,40 @@ struct Wavefront
     int32_t *h_ring = nullptr; // pinned: kRing snapshots of the device counters
     cudaEvent_t ring_ev[kRing] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int blocks_trace = 1, blocks_shadow = 1, blocks_shade = 1;
-    std::vector<cudaEvent_t> prof_ev; // TRT_RENDER_PROFILE: five timestamps per iteration, grown on demand
+    int blocks_walk = 1, blocks_shade = 1;
+    std::vector<cudaEvent_t> prof_ev; // TRT_RENDER_PROFILE: four timestamps per iteration, grown on demand
+    ~Wavefront()
+    {
+        for (void *p : allocs)
+            cudaFree(p);
+        if (h_ring)
+            cudaFreeHost(h_ring);
+        for (cudaEvent_t e : ring_ev)
+            if (e)
+                cudaEventDestroy(e);
+        for (cudaEvent_t e : {ev0, ev1})
+            if (e)
+                cudaEventDestroy(e);
+        for (cudaEvent_t e : prof_ev)
+            cudaEventDestroy(e);
+    }
 };
 
 void destroyWavefront(trt_scene *s)
 {
-    if (!s->wf)
-        return;
-    for (void *p : s->wf->allocs)
-        cudaFree(p);
-    if (s->wf->h_ring)
-        cudaFreeHost(s->wf->h_ring);
-    for (cudaEvent_t e : s->wf->ring_ev)
-        if (e)
-            cudaEventDestroy(e);
-    if (s->wf->ev0)
-        cudaEventDestroy(s->wf->ev0), cudaEventDestroy(s->wf->ev1);
-    for (cudaEvent_t e : s->wf->prof_ev)
-        cudaEventDestroy(e);
     delete s->wf;
     s->wf = nullptr;
 }
 
+// Path state for `paths` paths.  Built aside and published only when every allocation has succeeded, so that a
+// failed attempt (an explicit batch_paths beyond the free memory) leaves the scene without a wavefront and a retry
+// with a smaller batch starts clean.
 static int ensureWavefront(trt_scene *s, int paths)
 {
     if (s->wf && s->wf->capacity >= paths)
         return TRT_OK;
     destroyWavefront(s);
-    Wavefront *w = new Wavefront();
-    s->wf = w;
-    w->capacity = paths;
+    std::unique_ptr<Wavefront> w(new Wavefront());
     w->n_lights = std::max(1, s->view.n_lights);
     const size_t N = (size_t)paths, NL = N * w->n_lights;
     auto alloc = [&](void **p, size_t bytes) -> int {
@@ -655,16 +674,20 @@ static int ensureWavefront(trt_scene *s, int paths)
         (rc = alloc((void **)&b.sh_o, NL * 16)) || (rc = alloc((void **)&b.sh_d, NL * 16)) ||
         (rc = alloc((void **)&b.sh_contrib, NL * 16)) ||
         (rc = alloc((void **)&b.counters, kNumCounters * 4)))
+    {
+        cudaGetLastError(); // the failed cudaMalloc must not poison the next call
         return rc;
+    }
     TRT_CUDA(cudaMemset(b.counters, 0, kNumCounters * 4));
     TRT_CUDA(cudaMallocHost((void **)&w->h_ring, Wavefront::kRing * kNumCounters * 4));
     for (cudaEvent_t &e : w->ring_ev)
         TRT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     TRT_CUDA(cudaEventCreate(&w->ev0));
     TRT_CUDA(cudaEventCreate(&w->ev1));
-    TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w->blocks_trace, k_trace<0>, kBlock, 0));
-    TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w->blocks_shadow, k_shadow<0>, kBlock, 0));
+    TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w->blocks_walk, k_walk<0>, kBlock, 0));
     TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w->blocks_shade, k_shade, kShadeBlock, 0));
+    w->capacity = paths;
+    s->wf = w.release();
     return TRT_OK;
 }
 
@@ -677,31 +700,32 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
         setLastError("more than 32 lights");
         return TRT_ERR_LIMIT;
     }
-    // Paths in flight per batch.  Every depth iteration costs five launches and at least one wave of rays (~0.2 ms on
-    // staircase) whatever the queue length, and path counts decay by 0.8 per depth, so large batches amortise the
-    // long tail.  Measured: veach-mis 1280x720 256 spp 506.7 / 499.6 / 493.6 ms and staircase 1920x1080 128 spp
-    // 2127 / 2102 / 2094 ms at 32 / 64 / 128 Mi paths.  Default 128 Mi paths (52 GB of path state with 6 lights:
-    // HBM is 180 GB and the scene itself is megabytes), bounded by a third of the free memory.
-    long long target = p.batch_paths > 0 ? p.batch_paths : (128ll << 20);
+    const int nl = s->view.n_lights, nl1 = std::max(1, nl);
+    // Paths in flight per batch.  Path counts decay by 0.8 per depth and every depth costs two launches of at least one
+    // wave whatever the queue length, so a batch should be large against that tail — but the tail is short now (round 1
+    // paid five launches per depth and defaulted to 128 Mi paths = 52 GB with six lights for 2.6 % over 32 Mi).
+    // Default: 32 Mi paths (13 GB with six lights), bounded by a third of the free memory; batch_paths asks for more.
+    long long target = p.batch_paths > 0 ? p.batch_paths : (32ll << 20);
+    // walker tokens carry two flag bits, and slot * n_lights + light indexes the light-sample contributions
+    const long long max_paths = (long long)(kShadowBit - 1) / nl1;
     if (p.batch_paths <= 0)
     {
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
         {
-            const long long per_path = 100 + 48ll * std::max(1, s->view.n_lights);
+            const long long per_path = 100 + 48ll * nl1;
             const long long have = (long long)(s->wf ? (size_t)s->wf->capacity * per_path : 0);
             target = std::min(target, std::max(1ll << 20, ((long long)free_b / 3 + have) / per_path));
         }
-        // slot * n_lights + light must fit 32-bit indices (checked below for explicit batch sizes)
-        target = std::min(target, 0x7fffffffll / std::max(1, s->view.n_lights));
+        target = std::min(target, max_paths);
     }
     const int total_samples = p.sample_end - p.sample_begin;
     if (total_samples <= 0)
         return TRT_OK;
     int spb = (int)std::max(1ll, std::min((long long)total_samples, target / npix));
-    if (npix * spb > 0x7fffffffll / std::max(1, s->view.n_lights))
+    if (npix * spb > max_paths)
     {
-        setLastError("batch too large for 32-bit slot indices");
+        setLastError("batch too large for 30-bit ray tokens (paths x lights must stay below 2^30)");
         return TRT_ERR_LIMIT;
     }
     int rc = ensureWavefront(s, (int)(npix * spb));
@@ -710,19 +734,20 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
     Wavefront *w = s->wf;
     const WfBuffers &b = w->buf;
     const int mode = (p.flags & TRT_RENDER_REFTOPO) ? 1 : ((p.flags & TRT_RENDER_PLAIN) ? 2 : 0);
-    const int nl = s->view.n_lights;
     // The host never waits for an iteration it has just launched: every kernel reads its queue length from device
-    // memory, and the host looks at the counters of iteration it - kLag to learn when the batch has died out.
+    // memory, and the host looks at the counters of iteration it - kLag to learn when the batch has died out.  (At
+    // least one iteration is always launched after the one that emptied the queue: its k_walk serves the light
+    // samples of the last vertices.)
     constexpr int kLag = 2;
-    const unsigned grid_trace = (unsigned)(s->sm_count * std::max(1, w->blocks_trace));
-    const unsigned grid_shadow = (unsigned)(s->sm_count * std::max(1, w->blocks_shadow));
-    const unsigned grid_shade = (unsigned)(s->sm_count * 8);
+    static_assert(kLag >= 1, "the walk after the last k_shade serves its shadow rays");
+    const long long full_walk = (long long)s->sm_count * std::max(1, w->blocks_walk);
+    const long long full_plain = (long long)s->sm_count * 16;
     // k_shade: exactly the resident CTAs (grid-stride loop inside): a second, partly filled wave of CTAs would cost a
     // whole extra pass of ~40 us warp iterations
-    const unsigned grid_kshade = (unsigned)(s->sm_count * std::max(1, w->blocks_shade));
+    const long long full_shade = (long long)s->sm_count * std::max(1, w->blocks_shade);
     const bool profile = (p.flags & TRT_RENDER_PROFILE) != 0;
     size_t prof_used = 0;
-    double prof_ms[4] = {0, 0, 0, 0};
+    double prof_ms[3] = {0, 0, 0};
     auto stamp = [&]() -> int { // a timestamp on the stream between two launches
         if (prof_used == w->prof_ev.size())
         {
@@ -732,6 +757,17 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
         }
         TRT_CUDA(cudaEventRecord(w->prof_ev[prof_used++], stream));
         return TRT_OK;
+    };
+    auto walk = [&](int q, int what, long long rays_bound) {
+        // grids follow the queue: its length two iterations ago bounds it (queues only shrink)
+        const long long need = std::max(1ll, (rays_bound + kBlock - 1) / kBlock);
+        if (mode == 1)
+            k_walk<1><<<(unsigned)std::min(full_plain, need), kBlock, 0, stream>>>(s->view, b, q, what);
+        else if (mode == 2)
+            k_walk<2><<<(unsigned)std::min(full_plain, need), kBlock, 0, stream>>>(s->view, b, q, what);
+        else
+            k_walk<0><<<(unsigned)std::min(full_walk, need), kBlock, 0, stream>>>(s->view, b, q, what);
+        s->stats.kernel_launches++;
     };
     TRT_CUDA(cudaEventRecord(w->ev0, stream));
     for (int s0 = p.sample_begin; s0 < p.sample_end; s0 += spb)
@@ -744,6 +780,7 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
         s->stats.rays_closest += (uint64_t)n_paths; // iteration 0 traces every path's camera ray
         int q = 0, consumed = 0;
         bool dead = false;
+        long long live_bound = n_paths; // no queue from here on is longer
         auto consume = [&](int it) -> int { // counters as they stood after k_shade of iteration `it`
             TRT_CUDA(cudaEventSynchronize(w->ring_ev[it % Wavefront::kRing]));
             const int32_t *c = w->h_ring + (size_t)(it % Wavefront::kRing) * kNumCounters;
@@ -753,6 +790,7 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
                 shadow += (uint64_t)c[kShadowCount + l];
             s->stats.rays_shadow += shadow;
             s->stats.rays_closest += (uint64_t)next_live; // traced by iteration it + 1
+            live_bound = next_live;
             if (next_live == 0)
                 dead = true;
             return TRT_OK;
@@ -760,36 +798,30 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
         int depth = 0;
         for (; !dead; ++depth)
         {
-            const unsigned grid_plain = (unsigned)(s->sm_count * 16);
-            if (profile && (rc = stamp()))
-                return rc;
-            if (mode == 1)
-                k_trace<1><<<grid_plain, kBlock, 0, stream>>>(s->view, b, q);
-            else if (mode == 2)
-                k_trace<2><<<grid_plain, kBlock, 0, stream>>>(s->view, b, q);
+            // the shadow rays of this walk come from the previous depth's vertices: at most n_lights per path of a
+            // queue that was no longer than the bound either
+            const long long sh_bound = depth > 0 ? live_bound * nl : 0;
+            if (profile)
+            {
+                if ((rc = stamp()))
+                    return rc;
+                walk(q, 1, live_bound);
+                if ((rc = stamp()))
+                    return rc;
+                walk(q, 2 | 4, sh_bound);
+                if ((rc = stamp()))
+                    return rc;
+            }
             else
-                k_trace<0><<<grid_trace, kBlock, 0, stream>>>(s->view, b, q);
-            if (profile && (rc = stamp()))
-                return rc;
-            k_reset_counters<<<1, 32, 0, stream>>>(b, q ^ 1);
-            k_shade<<<grid_kshade, kShadeBlock, 0, stream>>>(s->view, b, q, depth, p.max_depth, s0, p.seed);
+                walk(q, 1 | 2 | 4, live_bound + sh_bound);
+            const long long shade_grid = std::min(full_shade, std::max(1ll, (live_bound + kShadeBlock - 1) / kShadeBlock));
+            k_shade<<<(unsigned)shade_grid, kShadeBlock, 0, stream>>>(s->view, b, q, depth, p.max_depth, s0, p.seed);
+            s->stats.kernel_launches++;
             TRT_CUDA(cudaMemcpyAsync(w->h_ring + (size_t)(depth % Wavefront::kRing) * kNumCounters, b.counters,
                                      kNumCounters * 4, cudaMemcpyDeviceToHost, stream));
             TRT_CUDA(cudaEventRecord(w->ring_ev[depth % Wavefront::kRing], stream));
             if (profile && (rc = stamp()))
                 return rc;
-            if (mode == 1)
-                k_shadow<1><<<grid_plain, kBlock, 0, stream>>>(s->view, b);
-            else if (mode == 2)
-                k_shadow<2><<<grid_plain, kBlock, 0, stream>>>(s->view, b);
-            else
-                k_shadow<0><<<grid_shadow, kBlock, 0, stream>>>(s->view, b);
-            if (profile && (rc = stamp()))
-                return rc;
-            k_accumulate<<<grid_shade, kBlock, 0, stream>>>(s->view, b, q);
-            if (profile && (rc = stamp()))
-                return rc;
-            s->stats.kernel_launches += 5;
             q ^= 1;
             if (depth >= kLag && (rc = consume(consumed++)))
                 return rc;
@@ -800,10 +832,10 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
                 return rc;
         if (profile)
         {
-            // five timestamps per iteration: trace | reset + shade + counter snapshot | shadow | accumulate
+            // four timestamps per iteration: closest-hit walk | shadow walk | shade + counter snapshot
             TRT_CUDA(cudaStreamSynchronize(stream));
-            for (size_t i = 0; i + 4 < prof_used; i += 5)
-                for (int k = 0; k < 4; ++k)
+            for (size_t i = 0; i + 3 < prof_used; i += 4)
+                for (int k = 0; k < 3; ++k)
                 {
                     float ms = 0;
                     TRT_CUDA(cudaEventElapsedTime(&ms, w->prof_ev[i + k], w->prof_ev[i + k + 1]));
@@ -811,7 +843,7 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
                 }
             prof_used = 0;
         }
-        k_deposit<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(b, d_accum, (int)npix, ns);
+        k_deposit<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(b, d_accum, (int)npix, ns, nl1);
         s->stats.kernel_launches++;
         TRT_CUDA(cudaGetLastError());
     }
@@ -820,8 +852,8 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
     float ms = 0;
     TRT_CUDA(cudaEventElapsedTime(&ms, w->ev0, w->ev1));
     s->stats.last_render_ms = ms;
-    s->stats.ms_trace = prof_ms[0], s->stats.ms_shade = prof_ms[1], s->stats.ms_shadow = prof_ms[2];
-    s->stats.ms_accumulate = prof_ms[3];
+    s->stats.ms_trace = prof_ms[0], s->stats.ms_shadow = prof_ms[1], s->stats.ms_shade = prof_ms[2];
+    s->stats.ms_accumulate = 0.0; // folded into k_shade / k_deposit (settleVertex)
     return TRT_OK;
 }
 

@@ -9,7 +9,8 @@
  * and every traversal / shading step then runs in hand-written sm_100a kernels.
  *
  * Conventions: every call returns 0 on success or a negative trt_status; trt_last_error() gives the text.
- * No call exits the process, none falls back to the CPU: without an sm_100 device trt_scene_create fails.
+ * No call exits the process (C++ exceptions are caught at the boundary and returned as codes), none falls back to
+ * the CPU: without an sm_100 device trt_scene_create fails.
  * Calls on one trt_scene must be serialised by the caller (the reference's main is single-threaded outside
  * its OpenMP loop, which this library replaces).  Plain pointers and sizes only — no C++ / torch types.
  */
@@ -23,14 +24,16 @@
 extern "C" {
 #endif
 
-#define TRT_VERSION 100
+#define TRT_VERSION 200
 
 typedef enum trt_status {
     TRT_OK = 0,
     TRT_ERR_INVALID = -1,   /* bad argument / inconsistent description            */
     TRT_ERR_NO_DEVICE = -2, /* no sm_100 GPU: there is deliberately no CPU path   */
     TRT_ERR_CUDA = -3,      /* a CUDA runtime call failed (text in trt_last_error) */
-    TRT_ERR_LIMIT = -4      /* a documented capacity limit was exceeded           */
+    TRT_ERR_LIMIT = -4,     /* a documented capacity limit was exceeded           */
+    TRT_ERR_NCCL = -5,      /* libnccl.so.2 could not be loaded, or an NCCL call failed (trt_render_multi) */
+    TRT_ERR_IO = -6         /* a checkpoint file could not be written / read / does not match the scene    */
 } trt_status;
 
 /* reference INF (bvh.h:5): distance reported for a miss */
@@ -96,7 +99,9 @@ typedef struct trt_scene trt_scene;
 
 /* ---- lifetime ------------------------------------------------------------------------------------ */
 
-/* Number of usable sm_100 devices (0 when none / no driver). */
+/* Number of sm_100 devices among the CUDA devices of this process (0 when none / no driver).  `device` arguments
+ * below are plain CUDA ordinals (cudaSetDevice numbering, after CUDA_VISIBLE_DEVICES): on a box that mixes GPU
+ * generations the usable ordinals need not be 0 .. count-1; trt_scene_create says so for an ordinal that is not sm_100. */
 int trt_device_count(void);
 
 /* Copies the description to `device` and builds the GPU acceleration layout from the reference topology.
@@ -104,6 +109,11 @@ int trt_device_count(void);
  * Replaces: nothing in the reference (there the Scene is used in place); called once after main.cpp:76. */
 int trt_scene_create(const trt_scene_desc *desc, int device, trt_scene **out);
 void trt_scene_destroy(trt_scene *scene);
+
+/* A copy of `scene` on another device, made from the device-resident arrays (device-to-device copies; the layouts
+ * are not rebuilt on the host): how the scene is replicated for trt_render_multi ("BVH build: host, once,
+ * broadcast by plain cudaMemcpy to each device").  The copy is independent of the original afterwards. */
+int trt_scene_replicate(const trt_scene *scene, int device, trt_scene **out);
 
 /* Page-locked host memory for ray / result buffers: the blocking entry points DMA straight from / to such
  * buffers; pageable buffers are staged through internal pinned chunks (one extra host copy). */
@@ -125,7 +135,9 @@ void trt_host_free(void *p);
  * overlaps copies with kernels; it returns after the results are in the output arrays. */
 int trt_trace_closest(trt_scene *scene, const float *rays6, size_t n, int32_t *tri_id, float *t, uint32_t flags);
 
-/* Asynchronous device-pointer form on a caller-provided CUDA stream (cudaStream_t passed as void*).    */
+/* Asynchronous device-pointer form on a caller-provided CUDA stream (cudaStream_t passed as void*).  Launches of one
+ * scene may be in flight on several streams at once (each takes its own ray-pool cursor from a ring of 64); the CALLS
+ * themselves must still be serialised by the caller like every call on a trt_scene. */
 int trt_trace_closest_async(trt_scene *scene, const float *d_rays6, size_t n, int32_t *d_tri_id, float *d_t,
                             uint32_t flags, void *stream);
 
@@ -134,6 +146,24 @@ int trt_trace_closest_async(trt_scene *scene, const float *d_rays6, size_t n, in
  * triangle.cpp:12-29 in double).  Host pointers. Either output may be NULL. */
 int trt_hit_attributes(trt_scene *scene, const float *rays6, const int32_t *tri_id, const float *t, size_t n,
                        float *hitpoint3, float *pn3);
+
+/* ---- shade: replaces PathTracing::shade (pathtracing.h:14, pathTracing.cpp:3-102) for a batch of hits ---------- */
+
+typedef struct trt_shade_params {
+    uint64_t seed;     /* Philox key; the stream of ray i is (seed; pixel = i, sample, bounce, slot)              */
+    int32_t sample;    /* sample index of the streams (lets a caller shade the same hits with fresh numbers)     */
+    int32_t max_depth; /* 0 = reference behaviour: Russian roulette only                                         */
+    uint32_t flags;    /* TRT_RENDER_REFTOPO / TRT_RENDER_PLAIN                                                  */
+    uint32_t _pad;
+} trt_shade_params;
+
+/* radiance3[i] = shade(hit_i, -direction_i): what the reference's recursive shade() returns for the HitRecord of ray i
+ * — emitted radiance on a light, else next-event estimation over the lights (XML order) plus the Russian-roulette
+ * bounce chain (nextRay / Sample / RR) — run as one wavefront that starts from the caller's hits instead of camera
+ * rays.  tri_id / t as trt_trace_closest returned them for rays6 (tri_id < 0: no hit, radiance 0 as main.cpp:99-101).
+ * Host pointers.  Not divided by anything. */
+int trt_shade(trt_scene *scene, const float *rays6, const int32_t *tri_id, const float *t, size_t n,
+              const trt_shade_params *params, float *radiance3);
 
 /* Work done by the default traversal on a host ray batch, summed over rays: out4 = {wide nodes visited, child
  * box tests, reference leaves scanned, triangles in those leaves}.  Reporting only (rays that take the strict
@@ -154,7 +184,10 @@ typedef struct trt_render_params {
 
 #define TRT_RENDER_REFTOPO 1u /* trace with the reference-topology kernel instead of the fast layout */
 #define TRT_RENDER_PLAIN 2u   /* fast layout, plain thread-per-ray traversal instead of the persistent walker */
-#define TRT_RENDER_PROFILE 4u /* time each kernel class with CUDA events (trt_stats.ms_*); the image is unchanged */
+#define TRT_RENDER_PROFILE 4u /* time each kernel class with CUDA events (trt_stats.ms_*); the image is unchanged.  The
+                                 closest-hit and the shadow rays of a depth are then walked in two launches instead of one */
+#define TRT_RENDER_PEER_REDUCE 8u /* trt_render_multi: sum the per-GPU buffers with this library's own kernel over NVLink
+                                     peer memory (fused with the resolve) instead of ncclReduce */
 
 /* Renders the sample range and writes the reference's image buffer: double[H*W*3], row-major RGB, rows
  * top to bottom, already divided by spp (main.cpp:74,101-108) — what imshow (main.cpp:19-42) consumes. */
@@ -169,6 +202,34 @@ int trt_render_accumulate(trt_scene *scene, const trt_render_params *params, dou
  * d_accum device pointer; image_rgb / rgb8 host pointers, either may be NULL. */
 int trt_resolve(trt_scene *scene, const double *d_accum, int32_t spp, double *image_rgb, uint8_t *rgb8,
                 void *stream);
+
+/* ---- multi-GPU render inside the library: replaces the reference's own fan-out, the OpenMP loop over samples of
+ * main.cpp:79-81.  scenes[i] are n scenes created from the SAME description on n different devices of one box (the
+ * scene is replicated; trt_scene_create once per device).  One host thread per GPU renders samples
+ * [sample_begin + i*k/n ..) of every pixel into that GPU's accumulation buffer (trt_render_accumulate), the buffers
+ * are summed onto scenes[0]'s device — ncclReduce(sum, float64, W*H*3) over NVLink on communicators from
+ * ncclCommInitAll (libnccl.so.2 is loaded on first use), or, with TRT_RENDER_PEER_REDUCE in params->flags, by one
+ * kernel of this library that reads the peers' buffers directly and resolves in the same pass — and scenes[0] resolves.
+ * image_rgb / rgb8 as trt_resolve (host pointers, either may be NULL).  n = 1 is trt_render.  With the peer reduce
+ * two scenes may share a device (NCCL refuses duplicate devices).  trt_stats of scenes[0]: last_render_ms covers all
+ * GPUs' renders, the reduce and the resolve; ray counts stay per scene. */
+int trt_render_multi(trt_scene *const *scenes, int32_t n, const trt_render_params *params, double *image_rgb,
+                     uint8_t *rgb8);
+
+/* ---- accumulation checkpoints (the reference writes its image once, main.cpp:114) --------------------
+ * A device accumulation buffer (what trt_render_accumulate adds into) created zeroed / released by the library, for
+ * hosts that do not link the CUDA runtime themselves. */
+double *trt_accum_create(trt_scene *scene);
+void trt_accum_destroy(trt_scene *scene, double *d_accum);
+/* Writes / reads the buffer and the progress it stands for to a file: samples [0, samples_done) of `spp` rendered with
+ * `seed` and `max_depth`.  A render resumed from a checkpoint — trt_accum_load, then trt_render_accumulate of
+ * [samples_done, spp) — gives the image of an uninterrupted one bit for bit (every pixel-sample has its own Philox
+ * stream, sums are double).  The file carries the frame size, a format version and a checksum: trt_accum_load fails
+ * with TRT_ERR_IO on a truncated / corrupted file or one made for another frame size. */
+int trt_accum_save(trt_scene *scene, const double *d_accum, int32_t samples_done, int32_t spp, uint64_t seed,
+                   int32_t max_depth, const char *path);
+int trt_accum_load(trt_scene *scene, const char *path, double *d_accum, int32_t *samples_done, int32_t *spp,
+                   uint64_t *seed, int32_t *max_depth);
 
 /* ---- introspection ------------------------------------------------------------------------------- */
 
@@ -187,7 +248,11 @@ typedef struct trt_stats {
     int32_t accel_needles; /* triangles left under their reference leaf's box (fast layout)               */
     /* device time per kernel class of the last render made with TRT_RENDER_PROFILE (CUDA events between the launches;
        the role the clock() prints of main.cpp:60-61,116-117 play in the reference), else 0 */
-    double ms_trace, ms_shade, ms_shadow, ms_accumulate;
+    double ms_trace, ms_shade, ms_shadow, ms_accumulate; /* ms_accumulate: always 0 since v200 (folded into the shade pass) */
+    /* rays that took the reference's own exhaustive walk instead of the fast layout: non-finite rays and origins beyond
+       8 x scene scale from the coordinate origin.  Exact results, but orders of magnitude slower per
+       ray — a large number here explains a slow trace.  Counted on the device, read by trt_get_stats. */
+    uint64_t rays_strict;
 } trt_stats;
 
 /* ---- host-only: build the GPU layouts for `desc` and verify their invariants (no device needed) ------------------

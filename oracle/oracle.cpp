@@ -576,6 +576,9 @@ V3 shade(const orc_scene &s, const Hit &rec, V3 wi, const Rng &rng, int depth, i
         double irow = row - std::floor(row), icol = col - std::floor(col);
         const Tex &tx = s.tex[m.texture];
         int r = irow * tx.rows, c = icol * tx.cols;
+        // row - floor(row) is exactly 1.0 for a tiny negative row (e.g. -1e-20): the reference then reads one row /
+        // column past the image (:24, undefined behaviour); restatement and GPU both clamp to the last texel
+        r = std::min(r, tx.rows - 1), c = std::min(c, tx.cols - 1);
         const uint8_t *px = &tx.bgr[((size_t)r * tx.cols + c) * 3];
         Kd.x = (double)px[2] / 255, Kd.y = (double)px[1] / 255, Kd.z = (double)px[0] / 255;
     }
@@ -893,6 +896,58 @@ void orc_render(orc_scene *s, int32_t spp, int32_t sample_begin, int32_t sample_
     }
     if (ray_counts)
         ray_counts[0] += c0, ray_counts[1] += c1;
+}
+
+void orc_render_pixels(orc_scene *s, int32_t spp, int32_t sample_begin, int32_t sample_end, int32_t max_depth,
+                       uint64_t seed, const int32_t *pixels, int32_t n_pixels, double *rgb_out, int32_t threads)
+{
+    if (threads > 0)
+        omp_set_num_threads(threads);
+    const int W = s->W;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int q = 0; q < n_pixels; q++)
+    {
+        const int pix = pixels[q], i = pix / W, j = pix % W;
+        for (int k = sample_begin; k < sample_end; k++) // main.cpp:81-108 for one pixel
+        {
+            Rng rng{seed, (uint32_t)pix, (uint32_t)k};
+            V3 S, d;
+            primaryRay(*s, i, j, rng, S, d);
+            Hit rec = traceRoot(*s, S, d);
+            V3 color;
+            if (rec.is_hit)
+                color = shade(*s, rec, -d, rng, 0, max_depth, nullptr) / (float)spp;
+            rgb_out[3 * (size_t)q + 0] += color.x;
+            rgb_out[3 * (size_t)q + 1] += color.y;
+            rgb_out[3 * (size_t)q + 2] += color.z;
+        }
+    }
+}
+
+void orc_shade_batch(orc_scene *s, const float *rays6, const int32_t *tri_id, const float *t, int64_t n, uint64_t seed,
+                     int32_t sample, int32_t max_depth, float *radiance3, int32_t threads)
+{
+    if (threads > 0)
+        omp_set_num_threads(threads);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < n; i++)
+    {
+        V3 L;
+        if (tri_id[i] >= 0)
+        {
+            const float *r = rays6 + 6 * i;
+            const V3 S(r[0], r[1], r[2]), d(r[3], r[4], r[5]);
+            const Tri &T = s->tris[tri_id[i]];
+            Hit rec; // the record traverseBVH would have returned for this ray (bvh.cpp:219-226)
+            rec.is_hit = true, rec.distance = t[i], rec.direction = d, rec.tri = tri_id[i], rec.emissive = T.emissive;
+            rec.hitpoint = S + d * t[i];
+            const V3 bc = findBaryCor(T, rec.hitpoint);
+            rec.pn = normalize((T.vn[0] * bc.x) + (T.vn[1] * bc.y) + (T.vn[2] * bc.z));
+            Rng rng{seed, (uint32_t)i, (uint32_t)sample};
+            L = shade(*s, rec, -d, rng, 0, max_depth, nullptr);
+        }
+        radiance3[3 * i] = L.x, radiance3[3 * i + 1] = L.y, radiance3[3 * i + 2] = L.z;
+    }
 }
 
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { philox(ctr, key, out); }

@@ -64,6 +64,18 @@ void orc_trace_counts(orc_scene *s, const float *rays6, int64_t n, int32_t mode,
 void orc_render(orc_scene *s, int32_t spp, int32_t sample_begin, int32_t sample_end, int32_t max_depth,
                 uint64_t seed, double *image, uint64_t *ray_counts, int32_t threads);
 
+/* The same loop for a chosen set of pixels (row-major pixel indices of the W x H frame): rgb_out[3*q..] += the
+ * pixel's colour.  The Philox stream is keyed by the pixel index, so these are exactly the pixels orc_render would
+ * produce — how the 1280x720 / 1920x1080 configs are checked without rendering two million pixels on the CPU. */
+void orc_render_pixels(orc_scene *s, int32_t spp, int32_t sample_begin, int32_t sample_end, int32_t max_depth,
+                       uint64_t seed, const int32_t *pixels, int32_t n_pixels, double *rgb_out, int32_t threads);
+
+/* shade(hit, wi) (pathTracing.cpp:3-102, pathtracing.h:14) for a batch of already-traced rays: ray i hit post-build
+ * triangle tri_id[i] at distance t[i] (miss: tri_id < 0 -> radiance 0, main.cpp:99-101); wi = -direction.  Stream of
+ * ray i: (seed; pixel = i, sample).  radiance3 = the returned colour, not divided by anything. */
+void orc_shade_batch(orc_scene *s, const float *rays6, const int32_t *tri_id, const float *t, int64_t n, uint64_t seed,
+                     int32_t sample, int32_t max_depth, float *radiance3, int32_t threads);
+
 /* One Philox4x32-10 block (known-answer tests) and the uniform double derived from a slot. */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 double orc_uniform(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t depth, uint32_t slot);

@@ -23,6 +23,7 @@ class Mat
 {
 public:
     int rows = 0, cols = 0;
+    unsigned char *data = nullptr; // cv::Mat::data: first byte of the (continuous) pixel buffer
     bool empty() const { return !buf || buf->empty(); }
     template <typename T>
     T &at(int r, int c) { return reinterpret_cast<T *>(buf->data())[(size_t)r * cols + c]; }
@@ -44,6 +45,7 @@ inline Mat imread(const std::string &path)
         if (fread(b->data(), 1, b->size(), f) == b->size())
         {
             m.buf = b;
+            m.data = b->data();
             m.rows = rc[0];
             m.cols = rc[1];
         }

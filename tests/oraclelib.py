@@ -40,6 +40,8 @@ def lib():
         L.orc_trace.argtypes = [vp, vp, i64, vp, vp, vp, vp, i32]
         L.orc_trace_counts.argtypes = [vp, vp, i64, i32, vp, vp, vp, i32]
         L.orc_render.argtypes = [vp, i32, i32, i32, i32, u64, vp, vp, i32]
+        L.orc_render_pixels.argtypes = [vp, i32, i32, i32, i32, u64, vp, i32, vp, i32]
+        L.orc_shade_batch.argtypes = [vp, vp, vp, vp, i64, u64, i32, i32, vp, i32]
         L.orc_philox4x32_10.argtypes = [vp, vp, vp]
         L.orc_uniform.restype = C.c_double
         L.orc_uniform.argtypes = [u64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
@@ -142,6 +144,22 @@ class OracleScene:
         lib().orc_render(self.h, spp, sample_begin, spp if sample_end is None else sample_end, max_depth, seed,
                          img.ctypes.data, counts, threads)
         return img, (counts[0], counts[1])
+
+    def render_pixels(self, pixels, spp, seed=0, max_depth=0, sample_begin=0, sample_end=None, threads=0):
+        """The colours orc_render would give the row-major pixel indices `pixels` of the W x H frame: (n, 3) float64."""
+        pixels = np.ascontiguousarray(pixels, np.int32)
+        out = np.zeros((len(pixels), 3), np.float64)
+        lib().orc_render_pixels(self.h, spp, sample_begin, spp if sample_end is None else sample_end, max_depth, seed,
+                                pixels.ctypes.data, len(pixels), out.ctypes.data, threads)
+        return out
+
+    def shade_batch(self, rays, ids, t, seed=0, sample=0, max_depth=0, threads=0):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        ids, t = np.ascontiguousarray(ids, np.int32), np.ascontiguousarray(t, np.float32)
+        out = np.zeros((len(rays), 3), np.float32)
+        lib().orc_shade_batch(self.h, rays.ctypes.data, ids.ctypes.data, t.ctypes.data, len(rays), seed, sample,
+                              max_depth, out.ctypes.data, threads)
+        return out
 
     def primary_ray(self, i, j, k, seed=0):
         r = np.zeros(6, np.float32)

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert decl == set(api.EXPORTS), decl ^ set(api.EXPORTS)
     for s in decl:
         assert hasattr(lib, s), s
-    assert lib.trt_version() == 100
+    assert lib.trt_version() == 200
 
 
 def test_sm100a_sass_is_embedded():
@@ -89,3 +89,34 @@ def test_headers_compile_as_plain_c(tmp_path):
     out = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only",
                           "-I", os.path.join(root, "include"), str(src)], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
+
+
+def test_inconsistent_descriptions_are_rejected_not_thrown(host_scenes):
+    """Negative counts and NULL arrays under a positive count come back as TRT_ERR_INVALID from the host-only entry
+    points too (no C++ exception crosses the C ABI; round-1 advisor finding)."""
+    import copy
+
+    lib = trt.load_library()
+    good = host_scenes["back"].desc
+    rep = api.LayoutReport()
+    assert lib.trt_layout_check(C.byref(good), C.byref(rep)) == 0
+    for field, value in (("n_textures", -1), ("n_lights", -3), ("n_light_tris", -1), ("n_tris", -5), ("n_nodes", -1),
+                         ("n_materials", 0), ("width", 1)):
+        d = api.SceneDesc.from_buffer_copy(good)
+        setattr(d, field, value)
+        assert lib.trt_layout_check(C.byref(d), C.byref(rep)) == -1, field
+        assert lib.trt_last_error()
+    d = api.SceneDesc.from_buffer_copy(good)
+    d.v = None
+    assert lib.trt_layout_check(C.byref(d), C.byref(rep)) == -1
+    h, view = C.c_void_p(), api.LayoutView()
+    assert lib.trt_layout_build(C.byref(d), C.byref(h), C.byref(view)) == -1
+    h2 = C.c_void_p()
+    rc = lib.trt_scene_create(C.byref(d), 0, C.byref(h2))
+    assert rc in (-1, -2) and not h2.value
+    # the new entry points refuse null / nonsense arguments the same way
+    assert lib.trt_render_multi(None, 0, None, None, None) == -1
+    assert lib.trt_shade(None, None, None, None, 0, None, None) == -1
+    assert lib.trt_accum_save(None, None, 0, 1, 0, 0, b"/tmp/x") == -1
+    assert lib.trt_accum_load(None, b"/tmp/x", None, None, None, None, None) == -1
+    assert not lib.trt_accum_create(None)

@@ -119,7 +119,7 @@ def test_loader_errors_are_reported(tmp_path):
         trt.HostScene.load(d + "/q.xml", d + "/missing.obj", d + "/q.mtl", d)
 
 
-@pytest.mark.parametrize("nq", (9, 40))
+@pytest.mark.parametrize("nq", (9, 40, 224))  # 224: 100 k triangles, the upper subtrees are built by forked tasks
 def test_from_arrays_matches_oracle_build(nq):
     """Synthetic meshes (BASELINE config 5) enter through trt_host_scene_from_arrays: same derived fields and the
     same topology as the oracle's restatement of scene.cpp:196-205 + bvh.cpp:16-144."""

@@ -14,6 +14,7 @@ TRACE_DEVICE_PTRS, TRACE_EXHAUSTIVE, TRACE_REFTOPO, TRACE_PLAIN, TRACE_POOLED = 
 RENDER_REFTOPO = 1
 RENDER_PLAIN = 2
 RENDER_PROFILE = 4
+RENDER_PEER_REDUCE = 8
 
 
 class TrtError(RuntimeError):
@@ -58,7 +59,12 @@ class Stats(C.Structure):
                 ("accel_nodes", C.c_int32), ("accel_leaves", C.c_int32), ("ref_depth", C.c_int32),
                 ("device", C.c_int32), ("accel_slivers", C.c_int32), ("accel_needles", C.c_int32),
                 ("ms_trace", C.c_double), ("ms_shade", C.c_double), ("ms_shadow", C.c_double),
-                ("ms_accumulate", C.c_double)]
+                ("ms_accumulate", C.c_double), ("rays_strict", C.c_uint64)]
+
+
+class ShadeParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("sample", C.c_int32), ("max_depth", C.c_int32), ("flags", C.c_uint32),
+                ("_pad", C.c_uint32)]
 
 
 class LayoutReport(C.Structure):
@@ -77,9 +83,10 @@ class LayoutView(C.Structure):
 
 
 # every symbol include/trt.h and include/trt_host.h declare (tests check the library exports all of them)
-EXPORTS = ["trt_device_count", "trt_scene_create", "trt_scene_destroy", "trt_host_alloc", "trt_host_free",
+EXPORTS = ["trt_device_count", "trt_scene_create", "trt_scene_replicate", "trt_scene_destroy", "trt_host_alloc", "trt_host_free",
            "trt_trace_closest", "trt_trace_closest_async", "trt_trace_counters", "trt_hit_attributes", "trt_render",
-           "trt_render_accumulate", "trt_resolve", "trt_layout_check", "trt_layout_build", "trt_layout_free", "trt_get_stats", "trt_reset_stats", "trt_last_error",
+           "trt_render_accumulate", "trt_resolve", "trt_render_multi", "trt_shade", "trt_accum_create", "trt_accum_destroy",
+           "trt_accum_save", "trt_accum_load", "trt_layout_check", "trt_layout_build", "trt_layout_free", "trt_get_stats", "trt_reset_stats", "trt_last_error",
            "trt_version", "trt_host_scene_load", "trt_host_scene_from_arrays", "trt_host_scene_desc",
            "trt_host_scene_faces", "trt_host_scene_material_name", "trt_host_scene_build_seconds",
            "trt_host_scene_free", "trt_host_scene_save", "trt_host_scene_load_cache", "trt_decode_jpeg", "trt_write_png", "trt_write_pfm"]
@@ -105,6 +112,7 @@ def load_library():
     vp, cp, i32, u32, sz = C.c_void_p, C.c_char_p, C.c_int32, C.c_uint32, C.c_size_t
     L.trt_last_error.restype = cp
     L.trt_scene_create.argtypes = [C.POINTER(SceneDesc), C.c_int, C.POINTER(vp)]
+    L.trt_scene_replicate.argtypes = [vp, C.c_int, C.POINTER(vp)]
     L.trt_scene_destroy.argtypes = [vp]
     L.trt_scene_destroy.restype = None
     L.trt_host_alloc.restype = vp
@@ -122,6 +130,14 @@ def load_library():
     L.trt_layout_free.restype = None
     L.trt_render_accumulate.argtypes = [vp, C.POINTER(RenderParams), vp, vp]
     L.trt_resolve.argtypes = [vp, vp, i32, vp, vp, vp]
+    L.trt_render_multi.argtypes = [C.POINTER(vp), i32, C.POINTER(RenderParams), vp, vp]
+    L.trt_shade.argtypes = [vp, vp, vp, vp, sz, C.POINTER(ShadeParams), vp]
+    L.trt_accum_create.restype = vp
+    L.trt_accum_create.argtypes = [vp]
+    L.trt_accum_destroy.restype = None
+    L.trt_accum_destroy.argtypes = [vp, vp]
+    L.trt_accum_save.argtypes = [vp, vp, i32, i32, C.c_uint64, i32, cp]
+    L.trt_accum_load.argtypes = [vp, cp, vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_uint64), C.POINTER(i32)]
     L.trt_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.trt_reset_stats.argtypes = [vp]
     L.trt_host_scene_load.argtypes = [cp, cp, cp, cp, C.c_int, C.POINTER(vp)]
@@ -301,15 +317,36 @@ class HostScene:
             pass
 
 
+def render_multi(devs, spp, seed=0, max_depth=0, flags=0, batch_paths=0, want_rgb8=False, out=None):
+    """trt_render_multi: the frame rendered by all of `devs` (DeviceScene replicas of one scene on different GPUs) inside
+    the library — one host thread per GPU over sample ranges, one reduce onto devs[0]'s GPU (ncclReduce, or the
+    library's own peer-memory kernel with RENDER_PEER_REDUCE), resolve there."""
+    d0 = devs[0]
+    img = d0._image_out(out)
+    rgb = np.empty((d0.height, d0.width, 3), np.uint8) if want_rgb8 else None
+    handles = (C.c_void_p * len(devs))(*[d.h for d in devs])
+    p = d0.params(spp, 0, spp, max_depth, seed, batch_paths, flags)
+    _check(d0.lib.trt_render_multi(handles, len(devs), C.byref(p), img.ctypes.data, rgb.ctypes.data if want_rgb8 else None),
+           "trt_render_multi")
+    return (img, rgb) if want_rgb8 else img
+
+
 class DeviceScene:
     """Device-resident scene: the GPU hot path (closest hit, render). Needs an sm_100 GPU."""
 
-    def __init__(self, host_scene, device=0):
+    def __init__(self, host_scene, device=0, _replica_of=None):
         self.lib = load_library()
         self.host = host_scene
         self.h = C.c_void_p()
-        _check(self.lib.trt_scene_create(C.byref(host_scene.desc), device, C.byref(self.h)), "trt_scene_create")
+        if _replica_of is None:
+            _check(self.lib.trt_scene_create(C.byref(host_scene.desc), device, C.byref(self.h)), "trt_scene_create")
+        else:
+            _check(self.lib.trt_scene_replicate(_replica_of.h, device, C.byref(self.h)), "trt_scene_replicate")
         self.width, self.height = host_scene.desc.width, host_scene.desc.height
+
+    def replicate(self, device):
+        """A copy of this scene on another GPU (trt_scene_replicate: device-to-device, no host rebuild of the layouts)."""
+        return DeviceScene(self.host, device, _replica_of=self)
 
     def trace_closest(self, rays, flags=0, out_id=None, out_t=None):
         """rays: (n,6) float32 host array. Returns (tri_id int32[n], t float32[n])."""
@@ -387,6 +424,36 @@ class DeviceScene:
         _check(self.lib.trt_resolve(self.h, d_accum_ptr, spp, img.ctypes.data,
                                     rgb.ctypes.data if want_rgb8 else None, stream), "trt_resolve")
         return (img, rgb) if want_rgb8 else img
+
+    def shade(self, rays, ids, t, seed=0, sample=0, max_depth=0, flags=0):
+        """PathTracing::shade for a batch of traced rays (trt_shade): (n, 3) float32 radiance, wi = -direction."""
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        ids, t = np.ascontiguousarray(ids, np.int32), np.ascontiguousarray(t, np.float32)
+        out = np.empty((len(rays), 3), np.float32)
+        p = ShadeParams(seed, sample, max_depth, flags, 0)
+        _check(self.lib.trt_shade(self.h, rays.ctypes.data, ids.ctypes.data, t.ctypes.data, len(rays), C.byref(p),
+                                  out.ctypes.data), "trt_shade")
+        return out
+
+    # ---- accumulation buffers and checkpoints (trt_accum_*)
+    def accum_create(self):
+        p = self.lib.trt_accum_create(self.h)
+        if not p:
+            raise TrtError("trt_accum_create failed: " + self.lib.trt_last_error().decode())
+        return p
+
+    def accum_destroy(self, d_accum):
+        self.lib.trt_accum_destroy(self.h, d_accum)
+
+    def accum_save(self, d_accum, samples_done, spp, path, seed=0, max_depth=0):
+        _check(self.lib.trt_accum_save(self.h, d_accum, samples_done, spp, seed, max_depth, path.encode()), "trt_accum_save")
+
+    def accum_load(self, path, d_accum):
+        """-> dict(samples_done, spp, seed, max_depth) of the checkpoint now in d_accum."""
+        a, b, c, d = C.c_int32(), C.c_int32(), C.c_uint64(), C.c_int32()
+        _check(self.lib.trt_accum_load(self.h, path.encode(), d_accum, C.byref(a), C.byref(b), C.byref(c), C.byref(d)),
+               "trt_accum_load")
+        return dict(samples_done=a.value, spp=b.value, seed=c.value, max_depth=d.value)
 
     def stats(self):
         s = Stats()

@@ -101,6 +101,7 @@ struct SceneView
     const int32_t *ref_leaf_parent; // per reference leaf: (parent's inner index << 1) | right-child bit, -1 if the leaf is the root
     int32_t check_leaf_box;     // 0 only when the whole scene is ONE reference leaf (scanned without a box test)
     float strict_origin_limit;  // rays starting farther than this from the coordinate origin take the strict walk
+    unsigned long long *strict_counter; // rays that took the exhaustive reference walk (trt_stats.rays_strict)
     float inv_cull_limit;       // |1/d| beyond this (incl. inf) makes a class-1 ray: culling reciprocal clamped, path gate
     int32_t n_tris;
     const TriGeom *tri_geom; // post-build order

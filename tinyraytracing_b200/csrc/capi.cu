@@ -3,9 +3,12 @@
 
 #include <algorithm>
 #include <memory>
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <new>
+#include <stdexcept>
 
 namespace trt
 {
@@ -14,17 +17,43 @@ void setLastError(const std::string &s) { g_lastError = s; }
 
 namespace
 {
+// dst: a pointer member of s->view (recorded, so that trt_scene_replicate can re-point the copy), or anything else
 template <typename T>
-int upload(trt_scene *s, const T *src, size_t count, const T **dst)
+int upload(trt_scene *s, const T *src, size_t count, const T **dst, int texture_index = -1)
 {
     *dst = nullptr;
     if (count == 0)
         return TRT_OK;
     void *p = nullptr;
     TRT_CUDA(cudaMalloc(&p, count * sizeof(T)));
-    s->allocations.push_back(p);
+    const char *view0 = reinterpret_cast<const char *>(&s->view), *d = reinterpret_cast<const char *>(dst);
+    const size_t off = (d >= view0 && d < view0 + sizeof(SceneView)) ? (size_t)(d - view0) : trt_scene::kNotInView;
+    s->allocations.push_back({p, count * sizeof(T), off, texture_index});
     TRT_CUDA(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
     *dst = static_cast<const T *>(p);
+    return TRT_OK;
+}
+
+int initStreams(trt_scene *s)
+{
+    cudaDeviceProp prop;
+    TRT_CUDA(cudaGetDeviceProperties(&prop, s->device));
+    s->sm_count = prop.multiProcessorCount;
+    TRT_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    TRT_CUDA(cudaStreamCreateWithFlags(&s->copy_in, cudaStreamNonBlocking));
+    TRT_CUDA(cudaStreamCreateWithFlags(&s->copy_out, cudaStreamNonBlocking));
+    TRT_CUDA(cudaEventCreate(&s->ev[0]));
+    TRT_CUDA(cudaEventCreate(&s->ev[1]));
+    return TRT_OK;
+}
+
+int newStrictCounter(trt_scene *s)
+{
+    void *p = nullptr;
+    TRT_CUDA(cudaMalloc(&p, sizeof(unsigned long long)));
+    s->allocations.push_back({p, sizeof(unsigned long long), offsetof(SceneView, strict_counter), -1});
+    TRT_CUDA(cudaMemset(p, 0, sizeof(unsigned long long)));
+    s->view.strict_counter = static_cast<unsigned long long *>(p);
     return TRT_OK;
 }
 
@@ -34,6 +63,60 @@ int fail(int code, const std::string &msg)
     return code;
 }
 
+// No C++ exception may unwind through the C ABI (the layout builders allocate large vectors and run std::async tasks):
+// every extern "C" body that can throw runs inside guarded().
+template <typename F>
+int guarded(const char *what, F &&body)
+{
+    try
+    {
+        return body();
+    }
+    catch (const std::bad_alloc &)
+    {
+        return fail(TRT_ERR_LIMIT, std::string(what) + ": out of host memory");
+    }
+    catch (const std::length_error &e)
+    {
+        return fail(TRT_ERR_LIMIT, std::string(what) + ": " + e.what());
+    }
+    catch (const std::exception &e)
+    {
+        return fail(TRT_ERR_INVALID, std::string(what) + ": " + e.what());
+    }
+    catch (...)
+    {
+        return fail(TRT_ERR_INVALID, std::string(what) + ": unknown exception");
+    }
+}
+
+// counts and the arrays they size: negative counts, or a NULL array where the count is positive, are rejected up front
+std::string validateDesc(const trt_scene_desc &d)
+{
+    if (d.n_tris < 0 || d.n_nodes < 0 || d.n_materials < 1 || d.n_lights < 0 || d.n_light_tris < 0 || d.n_textures < 0)
+        return "negative count (or no material)";
+    if (d.width < 2 || d.height < 2)
+        return "frame smaller than 2 x 2 (main.cpp:88-89 divides by W-1 and H-1)";
+    if ((long long)d.width * d.height > 0x3fffffffll)
+        return "frame larger than 2^30 pixels";
+    if (d.n_tris > 0 && (!d.v || !d.normal || !d.mtl))
+        return "triangle arrays missing";
+    if (d.n_nodes > 0 && (!d.node_box || !d.node_link))
+        return "node arrays missing";
+    if (!d.materials)
+        return "materials missing";
+    if (d.n_lights > 0 && !d.lights)
+        return "lights missing";
+    if (d.n_light_tris > 0 && (!d.light_v || !d.light_vn || !d.light_cum_area))
+        return "light triangle arrays missing";
+    if (d.n_textures > 0 && !d.textures)
+        return "textures missing";
+    for (int i = 0; i < d.n_tris; ++i)
+        if (d.mtl[i] < 0 || d.mtl[i] >= d.n_materials)
+            return "triangle material index out of range";
+    return "";
+}
+
 bool isSm100(int device)
 {
     cudaDeviceProp p;
@@ -41,6 +124,13 @@ bool isSm100(int device)
         return false;
     return p.major == 10; // the library ships sm_100a SASS only
 }
+
+// Rays that start farther than this many scene scales from the coordinate origin take the exhaustive reference walk.
+// The fast layout's boxes carry a pad of 256 ulp(scale) >= 128 x 2^-23 scale; the float rounding the pad has to absorb
+// (hit point S + d t, slab distances) is about 3 x 2^-23 (|S| + |hit - S|) <= 3 x 2^-23 x (8 + 9) scale = 51 x 2^-23
+// scale: a margin of 2.5 at the limit (round 1 stopped at 4 x scale; a camera a few object radii away from a small
+// centred object then sent every primary ray down the slow path).
+constexpr float kStrictOriginFactor = 8.0f;
 
 // staging for the blocking host-pointer entry point
 constexpr size_t kChunkRays = 1u << 19; // small chunks keep the un-overlapped head (first H2D) and tail (last kernel + D2H) short
@@ -83,8 +173,8 @@ trt_scene::~trt_scene()
         cudaSetDevice(device);
     cudaDeviceSynchronize();
     trt::destroyWavefront(this);
-    for (void *p : allocations)
-        cudaFree(p);
+    for (const Alloc &a : allocations)
+        cudaFree(a.p);
     cudaFree(d_counter);
     cudaFree(d_frame_image), cudaFree(d_frame_accum), cudaFree(d_frame_rgb8);
     for (int b = 0; b < 2; ++b)
@@ -141,13 +231,21 @@ void trt_host_free(void *p)
         cudaFreeHost(p);
 }
 
+static int sceneCreate(const trt_scene_desc *desc, int device, trt_scene **out);
+
 int trt_scene_create(const trt_scene_desc *desc, int device, trt_scene **out)
 {
     if (!desc || !out)
         return fail(TRT_ERR_INVALID, "trt_scene_create: null argument");
     *out = nullptr;
-    if (desc->n_tris < 0 || desc->n_nodes < 0 || desc->n_materials < 1 || desc->width < 2 || desc->height < 2)
-        return fail(TRT_ERR_INVALID, "trt_scene_create: inconsistent description");
+    return guarded("trt_scene_create", [&] { return sceneCreate(desc, device, out); });
+}
+
+static int sceneCreate(const trt_scene_desc *desc, int device, trt_scene **out)
+{
+    const std::string bad = validateDesc(*desc);
+    if (!bad.empty())
+        return fail(TRT_ERR_INVALID, "trt_scene_create: " + bad);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     {
@@ -168,17 +266,11 @@ int trt_scene_create(const trt_scene_desc *desc, int device, trt_scene **out)
     std::unique_ptr<trt_scene> s(new trt_scene());
     s->device = device;
     TRT_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    TRT_CUDA(cudaGetDeviceProperties(&prop, device));
-    s->sm_count = prop.multiProcessorCount;
-    TRT_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    TRT_CUDA(cudaStreamCreateWithFlags(&s->copy_in, cudaStreamNonBlocking));
-    TRT_CUDA(cudaStreamCreateWithFlags(&s->copy_out, cudaStreamNonBlocking));
-    TRT_CUDA(cudaEventCreate(&s->ev[0]));
-    TRT_CUDA(cudaEventCreate(&s->ev[1]));
+    int rc;
+    if ((rc = initStreams(s.get())))
+        return rc;
 
     SceneView &v = s->view;
-    int rc;
     if ((rc = upload(s.get(), ab.ref_nodes.data(), ab.ref_nodes.size(), &v.ref_nodes)))
         return rc;
     if ((rc = upload(s.get(), ab.tri_geom.data(), ab.tri_geom.size(), &v.tri_geom)))
@@ -209,7 +301,9 @@ int trt_scene_create(const trt_scene_desc *desc, int device, trt_scene **out)
         (rc = upload(s.get(), ab.ref_leaf_parent.data(), ab.ref_leaf_parent.size(), &v.ref_leaf_parent)))
         return rc;
     v.check_leaf_box = ab.root_is_reference_leaf ? 0 : 1;
-    v.strict_origin_limit = 4.0f * ab.scene_scale;
+    v.strict_origin_limit = kStrictOriginFactor * ab.scene_scale;
+    if ((rc = newStrictCounter(s.get())))
+        return rc;
     // b * inv and S * inv of the fused culling test stay below 4e30 for every box plane b and admitted origin S
     v.inv_cull_limit = 1.0e30f / std::max(ab.scene_scale, 1.0f);
 
@@ -243,17 +337,18 @@ int trt_scene_create(const trt_scene_desc *desc, int device, trt_scene **out)
         if (t.rows < 1 || t.cols < 1 || !t.bgr)
             return fail(TRT_ERR_INVALID, "trt_scene_create: empty texture");
         tex[i].rows = t.rows, tex[i].cols = t.cols;
-        if ((rc = upload(s.get(), t.bgr, (size_t)t.rows * t.cols * 3, &tex[i].bgr)))
+        if ((rc = upload(s.get(), t.bgr, (size_t)t.rows * t.cols * 3, &tex[i].bgr, i)))
             return rc;
     }
     if ((rc = upload(s.get(), tex.data(), tex.size(), &v.textures)))
         return rc;
+    s->host_textures = tex;
 
     std::vector<DeviceMaterial> mats(desc->n_materials);
     for (int i = 0; i < desc->n_materials; ++i)
     {
         const trt_material &m = desc->materials[i];
-        if (m.texture >= desc->n_textures)
+        if (m.texture >= desc->n_textures || m.texture < -1)
             return fail(TRT_ERR_INVALID, "trt_scene_create: material texture index out of range");
         mats[i].Kd = make_float3(m.Kd[0], m.Kd[1], m.Kd[2]);
         mats[i].Ks = make_float3(m.Ks[0], m.Ks[1], m.Ks[2]);
@@ -309,6 +404,61 @@ void trt_scene_destroy(trt_scene *s)
     delete s; // ~trt_scene releases every device / pinned allocation, stream and event
 }
 
+static int sceneReplicate(const trt_scene *src, int device, trt_scene **out)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev || !isSm100(device))
+    {
+        cudaGetLastError();
+        return fail(TRT_ERR_NO_DEVICE, "trt_scene_replicate: device is not an sm_100 (B200) GPU");
+    }
+    std::unique_ptr<trt_scene> s(new trt_scene());
+    s->device = device;
+    TRT_CUDA(cudaSetDevice(device));
+    int rc;
+    if ((rc = initStreams(s.get())))
+        return rc;
+    s->view = src->view;
+    s->width = src->width, s->height = src->height;
+    s->host_textures = src->host_textures;
+    s->stats = trt_stats{};
+    s->stats.accel_nodes = src->stats.accel_nodes, s->stats.accel_leaves = src->stats.accel_leaves;
+    s->stats.ref_depth = src->stats.ref_depth, s->stats.accel_slivers = src->stats.accel_slivers;
+    s->stats.accel_needles = src->stats.accel_needles, s->stats.device = device;
+    for (const trt_scene::Alloc &a : src->allocations)
+    {
+        if (a.view_offset == offsetof(SceneView, strict_counter) || a.view_offset == offsetof(SceneView, textures))
+            continue; // rebuilt below
+        void *p = nullptr;
+        TRT_CUDA(cudaMalloc(&p, a.bytes));
+        s->allocations.push_back({p, a.bytes, a.view_offset, a.texture_index});
+        // device to device (over NVLink when the two are peers, staged by the driver otherwise)
+        TRT_CUDA(cudaMemcpyPeer(p, device, a.p, src->device, a.bytes));
+        if (a.view_offset != trt_scene::kNotInView)
+            std::memcpy(reinterpret_cast<char *>(&s->view) + a.view_offset, &p, sizeof p);
+        else if (a.texture_index >= 0 && a.texture_index < (int)s->host_textures.size())
+            s->host_textures[a.texture_index].bgr = static_cast<const uint8_t *>(p);
+        else
+            return fail(TRT_ERR_INVALID, "trt_scene_replicate: allocation without an owner");
+    }
+    s->view.textures = nullptr;
+    if ((rc = upload(s.get(), s->host_textures.data(), s->host_textures.size(), &s->view.textures)))
+        return rc;
+    if ((rc = newStrictCounter(s.get())))
+        return rc;
+    TRT_CUDA(cudaDeviceSynchronize());
+    *out = s.release();
+    return TRT_OK;
+}
+
+int trt_scene_replicate(const trt_scene *src, int device, trt_scene **out)
+{
+    if (!src || !out)
+        return fail(TRT_ERR_INVALID, "trt_scene_replicate: null argument");
+    *out = nullptr;
+    return guarded("trt_scene_replicate", [&] { return sceneReplicate(src, device, out); });
+}
+
 int trt_trace_closest_async(trt_scene *s, const float *d_rays6, size_t n, int32_t *d_id, float *d_t, uint32_t flags,
                             void *stream)
 {
@@ -318,25 +468,8 @@ int trt_trace_closest_async(trt_scene *s, const float *d_rays6, size_t n, int32_
     return launchClosest(s, d_rays6, n, d_id, d_t, flags, static_cast<cudaStream_t>(stream));
 }
 
-int trt_trace_closest(trt_scene *s, const float *rays6, size_t n, int32_t *tri_id, float *t, uint32_t flags)
+static int traceHostPipelined(trt_scene *s, const float *rays6, size_t n, int32_t *tri_id, float *t, uint32_t flags)
 {
-    if (!s || (!rays6 && n))
-        return fail(TRT_ERR_INVALID, "trt_trace_closest: null argument");
-    TRT_CUDA(cudaSetDevice(s->device));
-    if (flags & TRT_TRACE_DEVICE_PTRS)
-    {
-        TRT_CUDA(cudaEventRecord(s->ev[0], s->stream));
-        int rc = launchClosest(s, rays6, n, tri_id, t, flags, s->stream);
-        if (rc)
-            return rc;
-        TRT_CUDA(cudaEventRecord(s->ev[1], s->stream));
-        TRT_CUDA(cudaStreamSynchronize(s->stream));
-        float ms = 0;
-        TRT_CUDA(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
-        s->stats.last_trace_ms = ms;
-        return TRT_OK;
-    }
-    // host pointers: chunked, double-buffered pipeline  H2D (copy_in) -> kernel (stream) -> D2H (copy_out)
     int rc = ensureStaging(s);
     if (rc)
         return rc;
@@ -395,6 +528,35 @@ int trt_trace_closest(trt_scene *s, const float *rays6, size_t n, int32_t *tri_i
     TRT_CUDA(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
     s->stats.last_trace_ms = ms;
     return TRT_OK;
+}
+
+int trt_trace_closest(trt_scene *s, const float *rays6, size_t n, int32_t *tri_id, float *t, uint32_t flags)
+{
+    if (!s || (!rays6 && n))
+        return fail(TRT_ERR_INVALID, "trt_trace_closest: null argument");
+    TRT_CUDA(cudaSetDevice(s->device));
+    if (flags & TRT_TRACE_DEVICE_PTRS)
+    {
+        TRT_CUDA(cudaEventRecord(s->ev[0], s->stream));
+        int rc = launchClosest(s, rays6, n, tri_id, t, flags, s->stream);
+        if (rc)
+            return rc;
+        TRT_CUDA(cudaEventRecord(s->ev[1], s->stream));
+        TRT_CUDA(cudaStreamSynchronize(s->stream));
+        float ms = 0;
+        TRT_CUDA(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
+        s->stats.last_trace_ms = ms;
+        return TRT_OK;
+    }
+    // host pointers: chunked, double-buffered pipeline  H2D (copy_in) -> kernel (stream) -> D2H (copy_out)
+    const int rc = traceHostPipelined(s, rays6, n, tri_id, t, flags);
+    if (rc != TRT_OK)
+    {
+        // copies into the caller's buffers may still be in flight: nothing of this call may touch them after it returns
+        cudaStreamSynchronize(s->copy_in), cudaStreamSynchronize(s->stream), cudaStreamSynchronize(s->copy_out);
+        cudaGetLastError();
+    }
+    return rc;
 }
 
 int trt_hit_attributes(trt_scene *s, const float *rays6, const int32_t *tri_id, const float *t, size_t n,
@@ -524,6 +686,10 @@ int trt_layout_check(const trt_scene_desc *desc, trt_layout_report *report)
 {
     if (!desc || !report)
         return fail(TRT_ERR_INVALID, "trt_layout_check: null argument");
+    return guarded("trt_layout_check", [&]() -> int {
+    const std::string bad = validateDesc(*desc);
+    if (!bad.empty())
+        return fail(TRT_ERR_INVALID, "trt_layout_check: " + bad);
     AccelBuild ab;
     std::string err = buildAccel(*desc, ab);
     if (!err.empty())
@@ -533,6 +699,7 @@ int trt_layout_check(const trt_scene_desc *desc, trt_layout_report *report)
     if (!err.empty())
         return fail(TRT_ERR_INVALID, "trt_layout_check: " + err);
     return TRT_OK;
+    });
 }
 
 struct trt_layout
@@ -544,6 +711,10 @@ int trt_layout_build(const trt_scene_desc *desc, trt_layout **out, trt_layout_vi
 {
     if (!desc || !out || !view)
         return fail(TRT_ERR_INVALID, "trt_layout_build: null argument");
+    return guarded("trt_layout_build", [&]() -> int {
+    const std::string bad = validateDesc(*desc);
+    if (!bad.empty())
+        return fail(TRT_ERR_INVALID, "trt_layout_build: " + bad);
     std::unique_ptr<trt_layout> l(new trt_layout());
     AccelBuild &ab = l->ab;
     const std::string err = buildAccel(*desc, ab);
@@ -558,7 +729,7 @@ int trt_layout_build(const trt_scene_desc *desc, trt_layout **out, trt_layout_vi
     view->n_ref_leaves = (int32_t)ab.ref_leaf_parent.size();
     view->n_ref_inner = (int32_t)ab.ref_nodes.size();
     view->check_leaf_box = ab.root_is_reference_leaf ? 0 : 1;
-    view->strict_origin_limit = 4.0f * ab.scene_scale;
+    view->strict_origin_limit = kStrictOriginFactor * ab.scene_scale;
     view->miss_key = TRT_MISS_KEY;
     view->wide_nodes = reinterpret_cast<const float *>(ab.wide_nodes.data());
     view->fast_geom = reinterpret_cast<const float *>(ab.fast_geom.data());
@@ -570,6 +741,7 @@ int trt_layout_build(const trt_scene_desc *desc, trt_layout **out, trt_layout_vi
     view->ref_nodes = reinterpret_cast<const float *>(ab.ref_nodes.data());
     *out = l.release();
     return TRT_OK;
+    });
 }
 
 void trt_layout_free(trt_layout *l) { delete l; }
@@ -579,6 +751,13 @@ int trt_get_stats(trt_scene *s, trt_stats *out)
     if (!s || !out)
         return fail(TRT_ERR_INVALID, "trt_get_stats: null argument");
     *out = s->stats;
+    if (s->view.strict_counter)
+    {
+        TRT_CUDA(cudaSetDevice(s->device));
+        unsigned long long c = 0;
+        TRT_CUDA(cudaMemcpy(&c, s->view.strict_counter, sizeof c, cudaMemcpyDeviceToHost)); // waits for the work in flight
+        out->rays_strict = c;
+    }
     return TRT_OK;
 }
 
@@ -587,6 +766,11 @@ int trt_reset_stats(trt_scene *s)
     if (!s)
         return fail(TRT_ERR_INVALID, "trt_reset_stats: null argument");
     s->stats.rays_closest = s->stats.rays_shadow = s->stats.paths = s->stats.kernel_launches = 0;
+    if (s->view.strict_counter)
+    {
+        TRT_CUDA(cudaSetDevice(s->device));
+        TRT_CUDA(cudaMemset(s->view.strict_counter, 0, sizeof(unsigned long long)));
+    }
     return TRT_OK;
 }
 }

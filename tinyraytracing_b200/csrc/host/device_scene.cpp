@@ -154,6 +154,12 @@ DeviceScene::DeviceScene(Scene &scene, BVHNode *root, int device) : scene_(&scen
         throw std::runtime_error(std::string("trt_scene_create: ") + trt_last_error());
 }
 
+DeviceScene::DeviceScene(const DeviceScene &src, int device, bool) : scene_(src.scene_)
+{
+    if (trt_scene_replicate(src.h_, device, &h_) != TRT_OK)
+        throw std::runtime_error(std::string("trt_scene_replicate: ") + trt_last_error());
+}
+
 DeviceScene::~DeviceScene() { trt_scene_destroy(h_); }
 
 std::vector<HitRecord> traverseBVH(const std::vector<Ray> &rays, DeviceScene &dev)
@@ -184,6 +190,7 @@ std::vector<HitRecord> traverseBVH(const std::vector<Ray> &rays, DeviceScene &de
         h.pn = vec3(pn[i * 3], pn[i * 3 + 1], pn[i * 3 + 2]);
         h.triangle = dev.scene().triangles[id[i]];
         h.triangle_index = id[i];
+        h.startpoint = rays[i].startpoint;
     }
     return out;
 }
@@ -197,6 +204,95 @@ void renderImage(DeviceScene &dev, int spp, double *image, uint64_t seed, int ma
     p.spp = spp, p.sample_begin = 0, p.sample_end = spp, p.max_depth = max_depth, p.seed = seed;
     if (trt_render(dev.handle(), &p, image) != TRT_OK)
         throw std::runtime_error(std::string("trt_render: ") + trt_last_error());
+}
+
+void renderImage(const std::vector<DeviceScene *> &devs, int spp, double *image, uint64_t seed, int max_depth, uint32_t flags)
+{
+    std::vector<trt_scene *> handles;
+    for (DeviceScene *d : devs)
+        handles.push_back(d->handle());
+    trt_render_params p;
+    std::memset(&p, 0, sizeof p);
+    p.spp = spp, p.sample_begin = 0, p.sample_end = spp, p.max_depth = max_depth, p.seed = seed, p.flags = flags;
+    if (trt_render_multi(handles.data(), (int32_t)handles.size(), &p, image, nullptr) != TRT_OK)
+        throw std::runtime_error(std::string("trt_render_multi: ") + trt_last_error());
+}
+
+int renderImageCheckpointed(DeviceScene &dev, int spp, double *image, const std::string &checkpoint, int every, uint64_t seed,
+                            int max_depth)
+{
+    trt_scene *h = dev.handle();
+    double *acc = trt_accum_create(h);
+    if (!acc)
+        throw std::runtime_error(std::string("trt_accum_create: ") + trt_last_error());
+    int done = 0, rendered = 0;
+    {
+        int32_t c_done = 0, c_spp = 0, c_depth = 0;
+        uint64_t c_seed = 0;
+        // a missing / foreign / damaged file simply means "start from sample 0" (and is overwritten below)
+        if (trt_accum_load(h, checkpoint.c_str(), acc, &c_done, &c_spp, &c_seed, &c_depth) == TRT_OK && c_spp == spp &&
+            c_seed == seed && c_depth == max_depth)
+            done = c_done;
+        else
+        {
+            trt_accum_destroy(h, acc);
+            if (!(acc = trt_accum_create(h)))
+                throw std::runtime_error(std::string("trt_accum_create: ") + trt_last_error());
+        }
+    }
+    every = std::max(1, every);
+    trt_render_params p;
+    std::memset(&p, 0, sizeof p);
+    p.spp = spp, p.max_depth = max_depth, p.seed = seed;
+    int rc = TRT_OK;
+    while (done < spp && rc == TRT_OK)
+    {
+        p.sample_begin = done, p.sample_end = std::min(spp, done + every);
+        if ((rc = trt_render_accumulate(h, &p, acc, nullptr)) != TRT_OK)
+            break;
+        rendered += p.sample_end - done;
+        done = p.sample_end;
+        rc = trt_accum_save(h, acc, done, spp, seed, max_depth, checkpoint.c_str());
+    }
+    if (rc == TRT_OK)
+        rc = trt_resolve(h, acc, spp, image, nullptr, nullptr);
+    const std::string err = rc == TRT_OK ? "" : trt_last_error();
+    trt_accum_destroy(h, acc);
+    if (rc != TRT_OK)
+        throw std::runtime_error("renderImageCheckpointed: " + err);
+    return rendered;
+}
+
+std::vector<vec3> shade(const std::vector<HitRecord> &records, DeviceScene &dev, uint64_t seed, int sample, int max_depth)
+{
+    const size_t n = records.size();
+    std::vector<float> r6(n * 6), t(n), rad(n * 3);
+    std::vector<int32_t> id(n);
+    for (size_t i = 0; i < n; ++i)
+    {
+        const HitRecord &h = records[i];
+        float *p = &r6[i * 6];
+        p[0] = h.startpoint.x, p[1] = h.startpoint.y, p[2] = h.startpoint.z;
+        p[3] = h.direction.x, p[4] = h.direction.y, p[5] = h.direction.z;
+        id[i] = h.is_hit ? h.triangle_index : -1;
+        t[i] = h.distance;
+    }
+    trt_shade_params sp;
+    std::memset(&sp, 0, sizeof sp);
+    sp.seed = seed, sp.sample = sample, sp.max_depth = max_depth;
+    if (trt_shade(dev.handle(), r6.data(), id.data(), t.data(), n, &sp, rad.data()) != TRT_OK)
+        throw std::runtime_error(std::string("shade: ") + trt_last_error());
+    std::vector<vec3> out(n);
+    for (size_t i = 0; i < n; ++i)
+        out[i] = vec3(rad[i * 3], rad[i * 3 + 1], rad[i * 3 + 2]);
+    return out;
+}
+
+vec3 shade(HitRecord &res, vec3 dir, DeviceScene &dev, uint64_t seed, int sample, int max_depth)
+{
+    HitRecord r = res;
+    r.direction = vec3(-dir.x, -dir.y, -dir.z); // the reference passes wi = -ray.direction (main.cpp:101)
+    return shade(std::vector<HitRecord>{r}, dev, seed, sample, max_depth)[0];
 }
 
 // triangle.cpp:12-29: least-squares solution of [v0 v1 v2; 1 1 1] b = [p; 1] in double, by the reference's own route

@@ -1,7 +1,10 @@
 // Drop-in driver: the reference's program (main.cpp:44-119) with the sample loop replaced by the GPU path.
 // Same stdin protocol (basedir, .mtl, .xml, .obj, SPP — main.cpp:46-55), same load order (:66-69), same
 // buildBVH call (:76), same gamma-2.2 8-bit PNG `<basedir>/image<SPP>.png` (:19-42).
-// Optional overrides that default to reference behaviour: TRT_SEED, TRT_MAX_DEPTH, TRT_DEVICE (environment).
+// Optional overrides that default to reference behaviour (environment): TRT_SEED, TRT_MAX_DEPTH, TRT_DEVICE;
+// TRT_DEVICES=0,1,... renders on several GPUs of the box (samples sharded, one reduce: trt_render_multi;
+// TRT_PEER_REDUCE=1 selects the library's peer-memory reduce instead of NCCL); TRT_CHECKPOINT=<file> with
+// TRT_CHECKPOINT_EVERY=<spp> (default 64) writes accumulation checkpoints and resumes from one (single GPU).
 #include "tinyrt.h"
 #include "png_writer.h"
 
@@ -9,6 +12,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <iostream>
+#include <memory>
 
 using namespace trt;
 
@@ -67,11 +71,50 @@ int main()
         uint64_t seed = (e = std::getenv("TRT_SEED")) ? std::strtoull(e, nullptr, 0) : 0;
         int max_depth = (e = std::getenv("TRT_MAX_DEPTH")) ? std::atoi(e) : 0;
         int device = (e = std::getenv("TRT_DEVICE")) ? std::atoi(e) : 0;
-        DeviceScene dev(scene, root, device);
-        renderImage(dev, SAMPLE, image.data(), seed, max_depth);
+        std::vector<int> devices;
+        if ((e = std::getenv("TRT_DEVICES")))
+            for (const char *q = e; *q;)
+            {
+                char *end;
+                const long v = std::strtol(q, &end, 10);
+                if (end == q)
+                    break;
+                devices.push_back((int)v);
+                q = (*end == ',') ? end + 1 : end;
+            }
+        if (devices.empty())
+            devices.push_back(device);
+        std::vector<std::unique_ptr<DeviceScene>> devs;
+        for (int d : devices) // the scene is replicated on every GPU: built and uploaded once, then copied device to device
+            devs.emplace_back(devs.empty() ? new DeviceScene(scene, root, d) : new DeviceScene(*devs[0], d, true));
+        DeviceScene &dev = *devs[0];
+        const char *ckpt = std::getenv("TRT_CHECKPOINT");
+        if (devs.size() > 1)
+        {
+            std::vector<DeviceScene *> ptrs;
+            for (auto &d : devs)
+                ptrs.push_back(d.get());
+            const bool peer = (e = std::getenv("TRT_PEER_REDUCE")) && std::atoi(e) != 0;
+            renderImage(ptrs, SAMPLE, image.data(), seed, max_depth, peer ? TRT_RENDER_PEER_REDUCE : 0u);
+            std::printf("rendered on %zu GPUs (%s reduce)\n", devs.size(), peer ? "peer-memory" : "NCCL");
+        }
+        else if (ckpt && *ckpt)
+        {
+            const int every = (e = std::getenv("TRT_CHECKPOINT_EVERY")) ? std::atoi(e) : 64;
+            const int fresh = renderImageCheckpointed(dev, SAMPLE, image.data(), ckpt, every, seed, max_depth);
+            std::printf("checkpoint %s: %d of %d samples rendered by this run\n", ckpt, fresh, SAMPLE);
+        }
+        else
+            renderImage(dev, SAMPLE, image.data(), seed, max_depth);
 
         trt_stats st;
         trt_get_stats(dev.handle(), &st);
+        for (size_t i = 1; i < devs.size(); ++i) // ray counts are per scene: sum the replicas'
+        {
+            trt_stats o;
+            trt_get_stats(devs[i]->handle(), &o);
+            st.rays_closest += o.rays_closest, st.rays_shadow += o.rays_shadow;
+        }
         std::printf("rays: %llu closest + %llu shadow, %.3f ms on device (%.1f Mrays/s)\n",
                     (unsigned long long)st.rays_closest, (unsigned long long)st.rays_shadow, st.last_render_ms,
                     (st.rays_closest + st.rays_shadow) / (st.last_render_ms * 1e3));

@@ -129,6 +129,7 @@ struct HitRecord // bvh.h:7-15
     vec3 hitpoint, direction, pn;
     Triangle triangle;
     int triangle_index = -1; // extra: position in scene.triangles (post-build)
+    vec3 startpoint;         // extra: origin of the ray that produced the record (shade() re-derives hitpoint from it)
 };
 
 // bvh.cpp:16-144 — same topology and the same in-place reorder of `triangles` as the reference
@@ -144,6 +145,8 @@ class DeviceScene
 {
 public:
     DeviceScene(Scene &scene, BVHNode *root, int device = 0);
+    // replica of `src` on another GPU (trt_scene_replicate: device-to-device copy, the layouts are not rebuilt)
+    DeviceScene(const DeviceScene &src, int device, bool replicate);
     ~DeviceScene();
     DeviceScene(const DeviceScene &) = delete;
     DeviceScene &operator=(const DeviceScene &) = delete;
@@ -175,7 +178,29 @@ std::unique_ptr<SceneArrays> makeSceneArrays(Scene &scene, const BVHNode *root);
 std::vector<HitRecord> traverseBVH(const std::vector<Ray> &rays, DeviceScene &dev);
 HitRecord traverseBVH(Ray ray, DeviceScene &dev);
 
+// ---- PathTracing (pathtracing.h:14-17) ------------------------------------------------------------------------------
+// shade() (pathTracing.cpp:3-102) on the GPU.  The batch form runs ONE wavefront from the given records (trt_shade):
+// next-event estimation over the lights, Russian roulette and the whole bounce chain, radiance per record, wi = the
+// negated ray direction as at main.cpp:101.  Random numbers: Philox stream (seed; record index, sample).  The
+// single-record form is the drop-in signature of pathtracing.h:17 and costs a wavefront per call: use the batch form in
+// loops.  Records must come from traverseBVH above (they carry triangle_index and startpoint).
+// RR / Sample / nextRay (pathtracing.h:14-16) have no callers in the reference other than shade() and nextRay()
+// themselves; they live inside the device shade kernel (csrc/wavefront.cu: k_shade, sampleLobe) and are not exported.
+std::vector<vec3> shade(const std::vector<HitRecord> &records, DeviceScene &dev, uint64_t seed = 0, int sample = 0,
+                        int max_depth = 0);
+vec3 shade(HitRecord &res, vec3 dir, DeviceScene &dev, uint64_t seed = 0, int sample = 0, int max_depth = 0);
+
 // The sample loop of main.cpp:79-113 (getRay + traverseBVH + shade + accumulate) on the GPU:
 // fills image[H*W*3] (double, divided by spp) exactly as the reference's `image` buffer.
 void renderImage(DeviceScene &dev, int spp, double *image, uint64_t seed = 0, int max_depth = 0);
+// The same loop fanned out over several GPUs of one box (the role of main.cpp:79-81's OpenMP loop over samples):
+// devs are replicas of one scene on different devices; trt_render_multi shards the samples, sums the per-GPU buffers
+// with one reduce (NCCL, or the library's peer-memory kernel with TRT_RENDER_PEER_REDUCE in flags) and resolves.
+void renderImage(const std::vector<DeviceScene *> &devs, int spp, double *image, uint64_t seed = 0, int max_depth = 0,
+                 uint32_t flags = 0);
+// Checkpointed form: renders `every` samples at a time, writing the accumulation buffer + progress to `checkpoint`
+// after each step (trt_accum_save); if the file exists and matches (frame size, spp, seed, max_depth) the render
+// resumes from it — bit-identical to an uninterrupted render.  Returns the number of samples rendered by THIS call.
+int renderImageCheckpointed(DeviceScene &dev, int spp, double *image, const std::string &checkpoint, int every,
+                            uint64_t seed = 0, int max_depth = 0);
 } // namespace trt

@@ -32,7 +32,18 @@ struct trt_scene
     int device = -1;
     int sm_count = 148;
     trt::SceneView view{};
-    std::vector<void *> allocations; // every cudaMalloc owned by the scene
+    // every cudaMalloc owned by the scene, with what trt_scene_replicate needs to rebuild it on another device:
+    // view_offset = byte offset of the SceneView pointer member that refers to it (kNotInView: a texture's pixels,
+    // referred to by texture_index of host_textures / the device texture table instead)
+    struct Alloc
+    {
+        void *p;
+        size_t bytes, view_offset;
+        int texture_index;
+    };
+    static constexpr size_t kNotInView = ~(size_t)0;
+    std::vector<Alloc> allocations;
+    std::vector<trt::DeviceTexture> host_textures; // the device texture table as uploaded (device pointers inside)
     cudaStream_t stream = nullptr;   // library-owned stream for the blocking entry points
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -43,7 +54,8 @@ struct trt_scene
     float *d_t[2] = {nullptr, nullptr};
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     size_t chunk_rays = 0;
-    unsigned int *d_counter = nullptr; // ray-pool counters of the persistent kernels
+    unsigned int *d_counter = nullptr; // ray-pool cursors of the persistent kernels: a ring, one slot per launch in flight
+    unsigned int counter_slot = 0;
     int persistent_blocks_per_sm = 1, pooled_blocks_per_sm = 1;
     trt::Wavefront *wf = nullptr;
     // frame buffers of trt_resolve / trt_render, allocated on first use and kept: a cudaMalloc / cudaFree pair per
@@ -65,5 +77,7 @@ int launchHitAttributes(trt_scene *s, const float *d_rays6, const int32_t *d_id,
 // wavefront.cu
 int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, cudaStream_t stream);
 int resolveImage(trt_scene *s, const double *d_accum, int spp, double *d_image, uint8_t *d_rgb8, cudaStream_t stream);
+int shadeBatch(trt_scene *s, const float *d_rays6, const int32_t *d_id, const float *d_t, size_t n, const trt_shade_params &p,
+               float *d_radiance3, cudaStream_t stream);
 void destroyWavefront(trt_scene *s);
 } // namespace trt

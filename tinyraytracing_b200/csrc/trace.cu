@@ -141,22 +141,26 @@ int launchClosest(trt_scene *s, const float *d_rays6, size_t n, int32_t *d_id, f
         k_closest<2><<<grid, kTraceBlock, 0, stream>>>(s->view, d_rays6, n, d_id, d_t);
     else
     {
+        constexpr unsigned kCursorRing = 64; // launches of one scene that may be in flight on different streams at once
         if (!s->d_counter)
         {
-            TRT_CUDA(cudaMalloc((void **)&s->d_counter, 256));
+            TRT_CUDA(cudaMalloc((void **)&s->d_counter, kCursorRing * sizeof(unsigned int)));
             TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->persistent_blocks_per_sm,
                                                                    k_closest_persistent<false>, kTraceBlock, 0));
             TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->pooled_blocks_per_sm, k_closest_persistent<true>,
                                                                    kTraceBlock, 0));
         }
-        TRT_CUDA(cudaMemsetAsync(s->d_counter, 0, 4, stream));
+        // every launch gets its own cursor: two traces enqueued on different streams overlap on the device and would
+        // otherwise advance / reset each other's
+        unsigned int *cursor = s->d_counter + (s->counter_slot++ % kCursorRing);
+        TRT_CUDA(cudaMemsetAsync(cursor, 0, 4, stream));
         const bool pooled = (flags & TRT_TRACE_POOLED) != 0;
         const int bps = pooled ? s->pooled_blocks_per_sm : s->persistent_blocks_per_sm;
         const unsigned pgrid = (unsigned)std::min<size_t>((size_t)s->sm_count * bps, grid);
         if (pooled)
-            k_closest_persistent<true><<<pgrid, kTraceBlock, 0, stream>>>(s->view, d_rays6, (unsigned int)n, d_id, d_t, s->d_counter);
+            k_closest_persistent<true><<<pgrid, kTraceBlock, 0, stream>>>(s->view, d_rays6, (unsigned int)n, d_id, d_t, cursor);
         else
-            k_closest_persistent<false><<<pgrid, kTraceBlock, 0, stream>>>(s->view, d_rays6, (unsigned int)n, d_id, d_t, s->d_counter);
+            k_closest_persistent<false><<<pgrid, kTraceBlock, 0, stream>>>(s->view, d_rays6, (unsigned int)n, d_id, d_t, cursor);
     }
     TRT_CUDA(cudaGetLastError());
     s->stats.kernel_launches++;

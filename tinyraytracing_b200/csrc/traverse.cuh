@@ -585,7 +585,10 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                     {
                         // rare: the reference's own walk, finished on the spot
                         if (cls != 3)
+                        {
+                            atomicAdd(sv.strict_counter, 1ull);
                             traceRefTopology<true>(sv, st.S, st.d, st.hit);
+                        }
                         else
                             traceRefTopology<false>(sv, st.S, st.d, st.hit);
                         rays.store(ray, st.hit);
@@ -729,7 +732,10 @@ __device__ __forceinline__ void traceClosest(const SceneView &sv, float3 S, floa
     if (cls == 3)
         traceRefTopology<false>(sv, S, d, hit);
     else if (cls == 2)
+    {
+        atomicAdd(sv.strict_counter, 1ull);
         traceRefTopology<true>(sv, S, d, hit);
+    }
     else
         traceWide<false>(sv, S, d, hit, nullptr, cls);
 }

@@ -336,7 +336,7 @@ __device__ __forceinline__ void settleVertex(const WfBuffers &wf, int n_lights, 
 }
 
 __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) k_shade(SceneView sv, WfBuffers wf, int qsel, int depth, int max_depth,
-                                                  int sample0, uint64_t seed)
+                                                  int sample0, uint64_t seed, int npix, int pixel0)
 {
   const int count = wf.counters[qsel];
   // warp-uniform grid-stride loop: the queue appends below are warp-collective
@@ -391,8 +391,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) k_shade(SceneVie
             }
             else
             {
-                const int npix = sv.cam.width * sv.cam.height;
-                Rng rng{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(slot % npix), (uint32_t)(sample0 + slot / npix),
+                Rng rng{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(pixel0 + slot % npix), (uint32_t)(sample0 + slot / npix),
                         (uint32_t)depth};
                 const float3 S = xyz(wf.ray_o[slot]), d = xyz(rd4);
                 const float3 wi = -d;
@@ -410,7 +409,9 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) k_shade(SceneVie
                     const double row = (ts.vt[1] * bx + ts.vt[3] * by) + ts.vt[5] * bz;
                     const double irow = row - floor(row), icol = col - floor(col);
                     const DeviceTexture tx = sv.textures[m_texture];
-                    const int r = (int)(irow * tx.rows), c = (int)(icol * tx.cols);
+                    // frac() of a tiny negative coordinate is exactly 1.0: the reference then reads past the image
+                    // (:24, undefined); the oracle and this kernel clamp to the last texel
+                    const int r = min((int)(irow * tx.rows), tx.rows - 1), c = min((int)(icol * tx.cols), tx.cols - 1);
                     const uint8_t *px = tx.bgr + ((size_t)r * tx.cols + c) * 3;
                     Kd = f3((float)((double)px[2] / 255), (float)((double)px[1] / 255), (float)((double)px[0] / 255));
                 }
@@ -593,6 +594,39 @@ __global__ void __launch_bounds__(256) k_deposit(WfBuffers wf, double *accum, in
     accum[(size_t)pix * 3 + 2] += b;
 }
 
+// ---- trt_shade: a wavefront that starts from caller-supplied hits instead of camera rays (pathtracing.h:14) ----
+__global__ void __launch_bounds__(kBlock) k_inject(WfBuffers wf, const float *__restrict__ rays6, const int32_t *__restrict__ id,
+                                                   const float *__restrict__ t, int n)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0 && threadIdx.x < kNumCounters)
+        wf.counters[threadIdx.x] = (threadIdx.x == 0) ? n : 0;
+    if (slot >= n)
+        return;
+    const float *r = rays6 + (size_t)slot * 6;
+    wf.ray_o[slot] = make_float4(r[0], r[1], r[2], 0.f);
+    // arrives like a camera ray: an emissive hit returns its radiance (pathTracing.cpp:9-12, main.cpp:101)
+    wf.ray_d[slot] = make_float4(r[3], r[4], r[5], __int_as_float(CAMERA));
+    wf.hit_id[slot] = id[slot];
+    wf.hit_t[slot] = t[slot];
+    wf.thr[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+    wf.L[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    wf.nee_mask[slot] = 0u;
+    wf.queue[0][slot] = slot;
+}
+
+__global__ void __launch_bounds__(kBlock) k_collect(WfBuffers wf, float *__restrict__ radiance3, int n, int n_lights)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n)
+        return;
+    float4 L = wf.L[slot];
+    const uint32_t pm = wf.nee_mask[slot];
+    if (pm)
+        settleVertex(wf, n_lights, slot, pm, wf.thr[slot], L);
+    radiance3[(size_t)slot * 3] = L.x, radiance3[(size_t)slot * 3 + 1] = L.y, radiance3[(size_t)slot * 3 + 2] = L.z;
+}
+
 __global__ void __launch_bounds__(256) k_resolve(const double *accum, size_t n, int spp, double *image, uint8_t *rgb8)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -691,24 +725,17 @@ static int ensureWavefront(trt_scene *s, int paths)
     return TRT_OK;
 }
 
-int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, cudaStream_t stream)
+// Paths in flight per batch.  Path counts decay by 0.8 per depth and every depth costs two launches of at least one
+// wave whatever the queue length, so a batch should be large against that tail — but the tail is short now (round 1
+// paid five launches per depth and defaulted to 128 Mi paths = 52 GB with six lights for 2.6 % over 32 Mi).
+// Default: 32 Mi paths (13 GB with six lights), bounded by a third of the free memory; batch_paths asks for more.
+static long long batchTarget(trt_scene *s, int batch_paths, long long &max_paths)
 {
-    const int W = s->width, H = s->height;
-    const long long npix = (long long)W * H;
-    if (s->view.n_lights > kMaxLights)
-    {
-        setLastError("more than 32 lights");
-        return TRT_ERR_LIMIT;
-    }
-    const int nl = s->view.n_lights, nl1 = std::max(1, nl);
-    // Paths in flight per batch.  Path counts decay by 0.8 per depth and every depth costs two launches of at least one
-    // wave whatever the queue length, so a batch should be large against that tail — but the tail is short now (round 1
-    // paid five launches per depth and defaulted to 128 Mi paths = 52 GB with six lights for 2.6 % over 32 Mi).
-    // Default: 32 Mi paths (13 GB with six lights), bounded by a third of the free memory; batch_paths asks for more.
-    long long target = p.batch_paths > 0 ? p.batch_paths : (32ll << 20);
+    const int nl1 = std::max(1, s->view.n_lights);
+    long long target = batch_paths > 0 ? batch_paths : (32ll << 20);
     // walker tokens carry two flag bits, and slot * n_lights + light indexes the light-sample contributions
-    const long long max_paths = (long long)(kShadowBit - 1) / nl1;
-    if (p.batch_paths <= 0)
+    max_paths = (long long)(kShadowBit - 1) / nl1;
+    if (batch_paths <= 0)
     {
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
@@ -719,21 +746,19 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
         }
         target = std::min(target, max_paths);
     }
-    const int total_samples = p.sample_end - p.sample_begin;
-    if (total_samples <= 0)
-        return TRT_OK;
-    int spb = (int)std::max(1ll, std::min((long long)total_samples, target / npix));
-    if (npix * spb > max_paths)
-    {
-        setLastError("batch too large for 30-bit ray tokens (paths x lights must stay below 2^30)");
-        return TRT_ERR_LIMIT;
-    }
-    int rc = ensureWavefront(s, (int)(npix * spb));
-    if (rc)
-        return rc;
+    return target;
+}
+
+// The depth loop over the n_paths paths that k_raygen / k_inject have just set up in queue 0 (slot = index).
+// Stream keys of slot: pixel = pixel0 + slot % npix, sample = sample0 + slot / npix.  first_walk = false: the hits of depth 0
+// are already in hit_id / hit_t (trt_shade).  prof_ms (TRT_RENDER_PROFILE) += {closest-hit walk, shadow walk, shade}.
+static int runDepthLoop(trt_scene *s, cudaStream_t stream, int n_paths, int npix, int pixel0, int sample0, uint64_t seed,
+                        int max_depth, uint32_t flags, bool first_walk, double *prof_ms)
+{
     Wavefront *w = s->wf;
     const WfBuffers &b = w->buf;
-    const int mode = (p.flags & TRT_RENDER_REFTOPO) ? 1 : ((p.flags & TRT_RENDER_PLAIN) ? 2 : 0);
+    const int nl = s->view.n_lights;
+    const int mode = (flags & TRT_RENDER_REFTOPO) ? 1 : ((flags & TRT_RENDER_PLAIN) ? 2 : 0);
     // The host never waits for an iteration it has just launched: every kernel reads its queue length from device
     // memory, and the host looks at the counters of iteration it - kLag to learn when the batch has died out.  (At
     // least one iteration is always launched after the one that emptied the queue: its k_walk serves the light
@@ -745,9 +770,9 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
     // k_shade: exactly the resident CTAs (grid-stride loop inside): a second, partly filled wave of CTAs would cost a
     // whole extra pass of ~40 us warp iterations
     const long long full_shade = (long long)s->sm_count * std::max(1, w->blocks_shade);
-    const bool profile = (p.flags & TRT_RENDER_PROFILE) != 0;
+    const bool profile = (flags & TRT_RENDER_PROFILE) != 0 && prof_ms;
     size_t prof_used = 0;
-    double prof_ms[3] = {0, 0, 0};
+    int rc;
     auto stamp = [&]() -> int { // a timestamp on the stream between two launches
         if (prof_used == w->prof_ev.size())
         {
@@ -769,6 +794,103 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
             k_walk<0><<<(unsigned)std::min(full_walk, need), kBlock, 0, stream>>>(s->view, b, q, what);
         s->stats.kernel_launches++;
     };
+    int q = 0, consumed = 0;
+    bool dead = false;
+    long long live_bound = n_paths; // no queue from here on is longer
+    auto consume = [&](int it) -> int { // counters as they stood after k_shade of iteration `it`
+        TRT_CUDA(cudaEventSynchronize(w->ring_ev[it % Wavefront::kRing]));
+        const int32_t *c = w->h_ring + (size_t)(it % Wavefront::kRing) * kNumCounters;
+        const int next_live = c[(it & 1) ^ 1];
+        uint64_t shadow = 0;
+        for (int l = 0; l < nl; ++l)
+            shadow += (uint64_t)c[kShadowCount + l];
+        s->stats.rays_shadow += shadow;
+        s->stats.rays_closest += (uint64_t)next_live; // traced by iteration it + 1
+        live_bound = next_live;
+        if (next_live == 0)
+            dead = true;
+        return TRT_OK;
+    };
+    int depth = 0;
+    for (; !dead; ++depth)
+    {
+        // the shadow rays of this walk come from the previous depth's vertices: at most n_lights per path of a
+        // queue that was no longer than the bound either
+        const long long sh_bound = depth > 0 ? live_bound * nl : 0;
+        const bool walk_closest = depth > 0 || first_walk;
+        if (profile)
+        {
+            if ((rc = stamp()))
+                return rc;
+            if (walk_closest)
+                walk(q, 1, live_bound);
+            if ((rc = stamp()))
+                return rc;
+            if (depth > 0)
+                walk(q, 2 | 4, sh_bound);
+            if ((rc = stamp()))
+                return rc;
+        }
+        else if (walk_closest || depth > 0)
+            walk(q, (walk_closest ? 1 : 0) | 2 | 4, live_bound + sh_bound);
+        const long long shade_grid = std::min(full_shade, std::max(1ll, (live_bound + kShadeBlock - 1) / kShadeBlock));
+        k_shade<<<(unsigned)shade_grid, kShadeBlock, 0, stream>>>(s->view, b, q, depth, max_depth, sample0, seed, npix, pixel0);
+        s->stats.kernel_launches++;
+        TRT_CUDA(cudaMemcpyAsync(w->h_ring + (size_t)(depth % Wavefront::kRing) * kNumCounters, b.counters,
+                                 kNumCounters * 4, cudaMemcpyDeviceToHost, stream));
+        TRT_CUDA(cudaEventRecord(w->ring_ev[depth % Wavefront::kRing], stream));
+        if (profile && (rc = stamp()))
+            return rc;
+        q ^= 1;
+        if (depth >= kLag && (rc = consume(consumed++)))
+            return rc;
+    }
+    // iterations launched after the batch died are no-ops on empty queues; drain their snapshots
+    for (; consumed < depth; ++consumed)
+        if ((rc = consume(consumed)))
+            return rc;
+    if (profile)
+    {
+        // four timestamps per iteration: closest-hit walk | shadow walk | shade + counter snapshot
+        TRT_CUDA(cudaStreamSynchronize(stream));
+        for (size_t i = 0; i + 3 < prof_used; i += 4)
+            for (int k = 0; k < 3; ++k)
+            {
+                float ms = 0;
+                TRT_CUDA(cudaEventElapsedTime(&ms, w->prof_ev[i + k], w->prof_ev[i + k + 1]));
+                prof_ms[k] += ms;
+            }
+    }
+    return TRT_OK;
+}
+
+int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, cudaStream_t stream)
+{
+    const int W = s->width, H = s->height;
+    const long long npix = (long long)W * H;
+    if (s->view.n_lights > kMaxLights)
+    {
+        setLastError("more than 32 lights");
+        return TRT_ERR_LIMIT;
+    }
+    const int nl1 = std::max(1, s->view.n_lights);
+    long long max_paths = 0;
+    const long long target = batchTarget(s, p.batch_paths, max_paths);
+    const int total_samples = p.sample_end - p.sample_begin;
+    if (total_samples <= 0)
+        return TRT_OK;
+    int spb = (int)std::max(1ll, std::min((long long)total_samples, target / npix));
+    if (npix * spb > max_paths)
+    {
+        setLastError("batch too large for 30-bit ray tokens (paths x lights must stay below 2^30)");
+        return TRT_ERR_LIMIT;
+    }
+    int rc = ensureWavefront(s, (int)(npix * spb));
+    if (rc)
+        return rc;
+    Wavefront *w = s->wf;
+    const WfBuffers &b = w->buf;
+    double prof_ms[3] = {0, 0, 0};
     TRT_CUDA(cudaEventRecord(w->ev0, stream));
     for (int s0 = p.sample_begin; s0 < p.sample_end; s0 += spb)
     {
@@ -778,71 +900,8 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
         s->stats.kernel_launches++;
         s->stats.paths += (uint64_t)n_paths;
         s->stats.rays_closest += (uint64_t)n_paths; // iteration 0 traces every path's camera ray
-        int q = 0, consumed = 0;
-        bool dead = false;
-        long long live_bound = n_paths; // no queue from here on is longer
-        auto consume = [&](int it) -> int { // counters as they stood after k_shade of iteration `it`
-            TRT_CUDA(cudaEventSynchronize(w->ring_ev[it % Wavefront::kRing]));
-            const int32_t *c = w->h_ring + (size_t)(it % Wavefront::kRing) * kNumCounters;
-            const int next_live = c[(it & 1) ^ 1];
-            uint64_t shadow = 0;
-            for (int l = 0; l < nl; ++l)
-                shadow += (uint64_t)c[kShadowCount + l];
-            s->stats.rays_shadow += shadow;
-            s->stats.rays_closest += (uint64_t)next_live; // traced by iteration it + 1
-            live_bound = next_live;
-            if (next_live == 0)
-                dead = true;
-            return TRT_OK;
-        };
-        int depth = 0;
-        for (; !dead; ++depth)
-        {
-            // the shadow rays of this walk come from the previous depth's vertices: at most n_lights per path of a
-            // queue that was no longer than the bound either
-            const long long sh_bound = depth > 0 ? live_bound * nl : 0;
-            if (profile)
-            {
-                if ((rc = stamp()))
-                    return rc;
-                walk(q, 1, live_bound);
-                if ((rc = stamp()))
-                    return rc;
-                walk(q, 2 | 4, sh_bound);
-                if ((rc = stamp()))
-                    return rc;
-            }
-            else
-                walk(q, 1 | 2 | 4, live_bound + sh_bound);
-            const long long shade_grid = std::min(full_shade, std::max(1ll, (live_bound + kShadeBlock - 1) / kShadeBlock));
-            k_shade<<<(unsigned)shade_grid, kShadeBlock, 0, stream>>>(s->view, b, q, depth, p.max_depth, s0, p.seed);
-            s->stats.kernel_launches++;
-            TRT_CUDA(cudaMemcpyAsync(w->h_ring + (size_t)(depth % Wavefront::kRing) * kNumCounters, b.counters,
-                                     kNumCounters * 4, cudaMemcpyDeviceToHost, stream));
-            TRT_CUDA(cudaEventRecord(w->ring_ev[depth % Wavefront::kRing], stream));
-            if (profile && (rc = stamp()))
-                return rc;
-            q ^= 1;
-            if (depth >= kLag && (rc = consume(consumed++)))
-                return rc;
-        }
-        // iterations launched after the batch died are no-ops on empty queues; drain their snapshots
-        for (; consumed < depth; ++consumed)
-            if ((rc = consume(consumed)))
-                return rc;
-        if (profile)
-        {
-            // four timestamps per iteration: closest-hit walk | shadow walk | shade + counter snapshot
-            TRT_CUDA(cudaStreamSynchronize(stream));
-            for (size_t i = 0; i + 3 < prof_used; i += 4)
-                for (int k = 0; k < 3; ++k)
-                {
-                    float ms = 0;
-                    TRT_CUDA(cudaEventElapsedTime(&ms, w->prof_ev[i + k], w->prof_ev[i + k + 1]));
-                    prof_ms[k] += ms;
-                }
-            prof_used = 0;
-        }
+        if ((rc = runDepthLoop(s, stream, n_paths, (int)npix, 0, s0, p.seed, p.max_depth, p.flags, true, prof_ms)))
+            return rc;
         k_deposit<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(b, d_accum, (int)npix, ns, nl1);
         s->stats.kernel_launches++;
         TRT_CUDA(cudaGetLastError());
@@ -854,6 +913,48 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
     s->stats.last_render_ms = ms;
     s->stats.ms_trace = prof_ms[0], s->stats.ms_shadow = prof_ms[1], s->stats.ms_shade = prof_ms[2];
     s->stats.ms_accumulate = 0.0; // folded into k_shade / k_deposit (settleVertex)
+    return TRT_OK;
+}
+
+// shade(hit, wi) for n already-traced rays (device pointers): radiance3[i] = what the reference's recursive shade()
+// returns for the record of ray i (pathTracing.cpp:3-102), wi = -direction.  Stream of ray i: pixel = first + i.
+int shadeBatch(trt_scene *s, const float *d_rays6, const int32_t *d_id, const float *d_t, size_t n, const trt_shade_params &p,
+               float *d_radiance3, cudaStream_t stream)
+{
+    if (s->view.n_lights > kMaxLights)
+    {
+        setLastError("more than 32 lights");
+        return TRT_ERR_LIMIT;
+    }
+    if (n == 0)
+        return TRT_OK;
+    const int nl1 = std::max(1, s->view.n_lights);
+    long long max_paths = 0;
+    const long long target = std::min<long long>(batchTarget(s, 0, max_paths), (long long)n);
+    int rc = ensureWavefront(s, (int)target);
+    if (rc)
+        return rc;
+    const WfBuffers &b = s->wf->buf;
+    if (n > 0x7fffffffull)
+    {
+        setLastError("trt_shade: more than 2^31 - 1 rays in one call");
+        return TRT_ERR_LIMIT;
+    }
+    for (size_t off = 0; off < n; off += (size_t)target)
+    {
+        const int m = (int)std::min<size_t>((size_t)target, n - off);
+        k_inject<<<(unsigned)((m + kBlock - 1) / kBlock), kBlock, 0, stream>>>(b, d_rays6 + off * 6, d_id + off, d_t + off, m);
+        s->stats.kernel_launches++;
+        s->stats.paths += (uint64_t)m;
+        // stream of ray i: pixel key = i = chunk offset + slot (npix = INT_MAX keeps slot % npix = slot, slot / npix = 0)
+        if ((rc = runDepthLoop(s, stream, m, 0x7fffffff, (int)off, p.sample, p.seed, p.max_depth,
+                               p.flags & ~TRT_RENDER_PROFILE, false, nullptr)))
+            return rc;
+        k_collect<<<(unsigned)((m + kBlock - 1) / kBlock), kBlock, 0, stream>>>(b, d_radiance3 + off * 3, m, nl1);
+        s->stats.kernel_launches++;
+        TRT_CUDA(cudaGetLastError());
+    }
+    TRT_CUDA(cudaStreamSynchronize(stream));
     return TRT_OK;
 }
 

@@ -8,8 +8,13 @@ A "step" is one pass of the closest-hit path over the whole batch.
   value     Mrays/s with rays and results resident in HBM (CUDA events on the launching stream)
   e2e       the same metric through the C-ABI call a host program makes (trt_trace_closest with pinned host
             buffers): H2D of the rays and D2H of ids + distances inside the timed region
-  roofline  dominant kernel (k_closest) against the measured HBM copy bandwidth, using the ALGORITHMIC bytes
-            per ray B = 48 + 32*A + 48*T of SURVEY §8d (A, T from profiles/algorithmic_work.json)
+  roofline  dominant kernel (k_closest_persistent) against the resource that binds it on this workload — the SM issue
+            slots times the lanes active per issued instruction (the 2 kB scene is served from L1; ncu metrics of the
+            shipped build in profiles/r02_ncu_metrics.json, recomputable from ms_per_step) — with the DRAM traffic ncu
+            measured beside it, and the SURVEY §8d HBM-denominated figure (B = 48 + 32*A + 48*T bytes per ray, A, T from
+            profiles/algorithmic_work.json) kept as roofline.survey_hbm for cross-config comparison
+  other_scenes  the same kernel on staircase and on the 10 M-triangle stress mesh (BASELINE config 5, the one config
+            whose scene exceeds L2), each with its ncu DRAM traffic against the measured HBM peak
   cpu_baseline / --impl reference: the UNMODIFIED reference traverseBVH (oracle/_ref/libref.so) on the box's
             host cores over a bounded sample of the same rays
 
@@ -39,6 +44,57 @@ WORKLOAD = ("16Mi-ray closest-hit batch (25% camera / 50% uniform-in-AABB / 25% 
 
 def env_int(k, d):
     return int(os.environ.get(k, d))
+
+
+def bench_config():
+    """`config` of the JSON line: the workload, spelled identically by both arms (--impl b200 / reference) so that the
+    driver can tell they ran the same thing; what differs between the arms (rays actually traced per step, threads,
+    traversal mode) is under `arm`."""
+    return {"workload": WORKLOAD, "scene": "example-scenes-cg22/test/back", "rays_per_batch": N_RAYS,
+            "ray_seed": "0x5EED0001 + rank", "resolution_of_camera_rays": "512x512",
+            "l2": "inputs (%d MB rays + %d MB results per batch) exceed the 126 MB L2" % (N_RAYS * 24 >> 20, N_RAYS * 8 >> 20)}
+
+
+def load_ncu_metrics(key):
+    """ncu metrics of the shipped build for one workload (tools/ncu_metrics.py -> profiles/r02_ncu_metrics.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_metrics.json")) as f:
+            return json.load(f)[key]
+    except Exception:
+        return None
+
+
+def sm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["sm_max_mhz"])
+    except Exception:
+        return 1965.0
+
+
+def issue_roofline(key, rays, ms, sm_mhz, n_sm=148):
+    """The kernel against the SM issue slots: a B200 SM issues at most 4 warp instructions per cycle (one per
+    sub-partition), each serving up to 32 lanes.  warp instructions / ray and lanes / instruction come from the committed
+    ncu capture of the shipped build; the rate is this run's.  frac = issue-slot utilisation x lanes / 32 = the fraction
+    of the machine's thread-instruction throughput that does work."""
+    m = load_ncu_metrics(key)
+    if not m:
+        return None
+    clock = (sm_mhz or sm_peak()) * 1e6
+    rays_per_s = rays / (ms * 1e-3)
+    slots = n_sm * 4 * clock
+    issue = m["warp_inst_per_ray"] * rays_per_s / slots
+    achieved = m["warp_inst_per_ray"] * m["lanes_per_inst"] * rays_per_s
+    traffic = (m["dram_bytes_read"] + m["dram_bytes_write"]) * (rays / float(m["rays_per_launch"]))
+    peak_gbs, which = measured_peak_gbs()
+    return {"bound": "issue", "achieved": achieved / 1e12, "peak": slots * 32 / 1e12, "unit": "Tthread-inst/s",
+            "frac": achieved / (slots * 32), "traffic": traffic, "kernel": m.get("kernel", "k_closest_persistent"),
+            "issue_slot_frac": issue, "lanes_per_inst": m["lanes_per_inst"], "warp_inst_per_ray": m["warp_inst_per_ray"],
+            "ncu_issue_active_pct": m.get("issue_active_pct"), "sm_mhz_used": clock / 1e6,
+            "dram": {"achieved": traffic / (ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": traffic / (ms * 1e-3) / 1e9 / peak_gbs, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
+                     "note": "ncu dram__bytes_read.sum + dram__bytes_write.sum of the same launch, scaled to this batch"},
+            "source": "profiles/r02_ncu_metrics.json: " + m.get("capture", "")}
 
 
 def load_algorithmic_work(scene):
@@ -243,10 +299,74 @@ def run_reference(args):
             "impl": "reference", "metric": "Mrays/s (closest-hit)", "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_step": n, "host_threads": cores},
+            "config": bench_config(), "arm": {"rays_per_step": n, "host_threads": cores},
             "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
     return 0
+
+
+def bind_near_gpu(index):
+    """Run this process on the CPUs of the NUMA node the GPU hangs off, so that the page-locked ray / result buffers
+    allocated next live in that node's memory: with one process per GPU the host legs of eight e2e pipelines otherwise
+    cross the socket interconnect (round 1: 52 GB/s H2D per GPU at N = 1, 15.6 GB/s at N = 8).  Returns what it did and
+    the previous affinity (restored before the CPU baseline, which wants every core)."""
+    old = os.sched_getaffinity(0)
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read())
+        if node < 0:
+            return {"numa_node": None, "note": "the platform reports no NUMA node for %s" % bdf}, old
+        cpus = set()
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= old
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        nodes = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")])
+        return {"numa_node": node, "numa_nodes": nodes, "cpus_bound": len(cpus), "pci": bdf}, old
+    except Exception as e:  # containers without sysfs, non-Linux: leave the affinity alone
+        return {"numa_node": None, "note": "not bound: %s" % e}, old
+
+
+def link_ceiling(n, steps, world, barrier):
+    """What the host link allows for one e2e step: plain page-locked cudaMemcpyAsync of the same byte counts (24 B in,
+    8 B out per ray), both directions at once on two streams, every rank at the same time — no kernel, no chunking."""
+    import torch
+    import torch.distributed as dist
+
+    h_in = torch.empty(n * 24, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(n * 8, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(n * 24, dtype=torch.uint8, device="cuda")
+    d_out = torch.zeros(n * 8, dtype=torch.uint8, device="cuda")
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def once():
+        with torch.cuda.stream(s_in):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            h_out.copy_(d_out, non_blocking=True)
+        s_in.synchronize()
+        s_out.synchronize()
+
+    for _ in range(2):
+        once()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        once()
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    if world > 1:
+        tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm.item())
+    return {"ms_per_step": ms, "h2d_gbs_per_gpu": n * 24 / (ms * 1e-3) / 1e9, "d2h_gbs_per_gpu": n * 8 / (ms * 1e-3) / 1e9,
+            "what": "pinned cudaMemcpyAsync of the same bytes, H2D and D2H concurrently, all %d ranks at once (max over ranks)" % world}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -264,6 +384,7 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = trt.load_library()
+    numa, old_affinity = bind_near_gpu(local)
     with tempfile.TemporaryDirectory() as tmp:
         f = materialize_scene(tmp)
         devnull = os.open(os.devnull, os.O_WRONLY)
@@ -336,6 +457,11 @@ def run_gpu(args):
 
         ms_res, clocks, launches = timed(step_resident, events=True)
         ms_e2e, clocks_e2e, _ = timed(step_e2e, events=False)
+        link = link_ceiling(n, max(3, min(args.steps, 10)), world, barrier)
+        try:
+            os.sched_setaffinity(0, old_affinity)  # the CPU legs below want every core
+        except Exception:
+            pass
 
         # sanity of what was timed: results of both legs agree and really hit geometry
         ids_host = np.ctypeslib.as_array(C.cast(p_id, C.POINTER(C.c_int32)), (n,))
@@ -349,11 +475,12 @@ def run_gpu(args):
             "metric": "Mrays/s (closest-hit)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": n, "hit_fraction": hit_fraction,
-                       "l2": "inputs (%d MB rays + %d MB results per step) exceed the 126 MB L2" % (n * 24 >> 20, n * 8 >> 20),
-                       "traversal": {0: "default", 2: "exhaustive", 4: "reftopo"}.get(args.flags, str(args.flags))},
+            "config": bench_config(),
+            "arm": {"rays_per_step_per_gpu": n, "hit_fraction": hit_fraction,
+                    "traversal": {0: "default", 2: "exhaustive", 4: "reftopo"}.get(args.flags, str(args.flags))},
             "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": n * 24 * world, "d2h_bytes_per_step": n * 8 * world,
                     "ms_per_step": ms_e2e / args.steps, "timer": "host wall clock around the blocking C-ABI call",
+                    "link": link, "link_frac": link["ms_per_step"] / (ms_e2e / args.steps), "host_placement": numa,
                     "bound": "host link: %.1f GB/s H2D + %.1f GB/s D2H per GPU (24 B in, 8 B out per ray); the kernel itself "
                              "needs %.1f %% of the step" % (n * 24 / (ms_e2e / args.steps * 1e-3) / 1e9,
                                                            n * 8 / (ms_e2e / args.steps * 1e-3) / 1e9,
@@ -363,16 +490,21 @@ def run_gpu(args):
         }
         work = load_algorithmic_work(SCENE)
         peak, which = measured_peak_gbs()
+        roof = issue_roofline(SCENE, n, ms_res / args.steps, clocks.get("sm_mhz")) or {
+            "bound": "issue", "achieved": None, "peak": None, "unit": "Tthread-inst/s", "frac": None, "traffic": load_traffic(SCENE, n),
+            "note": "profiles/r02_ncu_metrics.json missing: no ncu capture of this build to read the instruction counts from"}
         if work:
             A, T = work
             bytes_per_ray = 48 + 32 * A + 48 * T
             achieved = bytes_per_ray * n / (ms_res / args.steps * 1e-3) / 1e9  # per launch = per step on one GPU
-            out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                               "traffic": load_traffic(SCENE, n), "kernel": "k_closest_persistent",
-                               "algorithmic_bytes_per_launch": bytes_per_ray * n, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
-                               "bytes_per_ray": bytes_per_ray, "A": A, "T": T,
-                               "layout": layout_roofline(dev, rays, n, ms_res / args.steps, peak),
-                               "note": "scene is L1/L2 resident (2 kB): the HBM-denominated figure is for cross-config comparison, SURVEY §8d"}
+            roof["survey_hbm"] = {"achieved": achieved, "peak": peak, "unit": "GB/s", "ratio": achieved / peak,
+                                  "algorithmic_bytes_per_launch": bytes_per_ray * n, "bytes_per_ray": bytes_per_ray, "A": A, "T": T,
+                                  "layout": layout_roofline(dev, rays, n, ms_res / args.steps, peak),
+                                  "note": "SURVEY §8d's cross-config figure: algorithmic bytes of the ordered-pruned walk of the "
+                                          "REFERENCE topology / measured HBM copy bandwidth. NOT a roofline fraction for this "
+                                          "scene: the 2 kB scene is served from L1, so the ratio exceeds 1 by construction; the "
+                                          "DRAM the kernel really moves is roofline.dram"}
+        out["roofline"] = roof
         if not args.no_render:
             out["render"] = render_measurements(args, tmp, rank, world, local, barrier)
             if rank == 0 and world == 1:
@@ -380,6 +512,8 @@ def run_gpu(args):
         if rank == 0 and world == 1 and not args.no_cpu:
             t_host = np.ctypeslib.as_array(C.cast(p_t, C.POINTER(C.c_float)), (n,))
             out["cpu_baseline"] = cpu_baseline(f, rays, ids_host, t_host, host)
+        if rank == 0 and world == 1 and not args.no_render:
+            out["other_scenes"] = other_scene_measurements(args, tmp)
         if args.extra and rank == 0 and world == 1:
             out["extra"] = extra_measurements(args, tmp)
         for p in (p_rays, p_id, p_t):
@@ -453,9 +587,25 @@ def cpu_baseline(files, rays, gpu_ids=None, gpu_t=None, host=None):
     return out
 
 
+def frame_hashes(img, rgb8=None):
+    """What a reader needs to tell that two runs produced the same picture: the 8-bit gamma-packed frame is identical
+    for any GPU count (the float64 sums differ in their last bits with the order of the per-GPU partial sums)."""
+    import hashlib
+
+    if rgb8 is None:  # imshow's formula, main.cpp:30-38
+        rgb8 = np.clip(np.power(img, np.float64(np.float32(1.0) / np.float32(2.2))) * 255, 0, 255).astype(np.uint8)
+    return {"frame_rgb8_sha256": hashlib.sha256(np.ascontiguousarray(rgb8).tobytes()).hexdigest()[:16],
+            "frame_f64_sha256": hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest()[:16],
+            "image_mean": float(img.mean())}
+
+
 def render_measurements(args, tmp, rank, world, local, barrier):
-    """BASELINE configs 3 / 4: full renders, samples sharded over the ranks, ONE NCCL sum-reduce of the accumulation
-    buffers, resolve on rank 0.  spp/s = spp / (max-over-ranks device time incl. the reduce)."""
+    """BASELINE configs 1 / 3 / 4: full renders with the samples sharded over the GPUs and ONE sum-reduce of the
+    accumulation buffers, resolve on GPU 0.  spp/s = spp / device time including the reduce and the resolve.
+    N = 1: trt_render.  N > 1: INSIDE the library (trt_render_multi: rank 0's process drives all N GPUs — one host thread
+    per GPU, scene replicated device to device, ncclCommInitAll + ncclReduce(sum, f64), and the library's own peer-memory
+    reduce + resolve kernel measured beside it) while the other ranks wait on the rendezvous store without touching their
+    GPUs; the round-1 path (one process per GPU, torch.distributed reduce) is timed beside it on config 3."""
     import torch
     import torch.distributed as dist
 
@@ -466,6 +616,7 @@ def render_measurements(args, tmp, rank, world, local, barrier):
     cfgs = [("config1_cornell_shell", "back", 512, 512, 16), ("config3_veach_mis", "veach-mis", 1280, 720, args.spp3)]
     if world == 8 or args.config4:
         cfgs.append(("config4_staircase", "staircase", 1920, 1080, args.spp4))
+    store = dist.distributed_c10d._get_default_store() if world > 1 else None
     out = {}
     for key, name, w, h, spp in cfgs:
         f = scenes.materialize(name, os.path.join(tmp, "r_%s_%d" % (name, rank)), width=w, height=h)
@@ -478,43 +629,152 @@ def render_measurements(args, tmp, rank, world, local, barrier):
             os.dup2(saved, 1)
         dev = trt.DeviceScene(host, local)
         frame = dev.pinned_image()  # the frame lands in page-locked host memory (valid until dev.close())
-        render_on_gpus(dev, spp, seed=2, out=frame)  # warm-up at full size: allocates the wavefront buffers, primes NCCL
-        # median of three timed renders for the sub-second configs (a one-off 100 ms stall was seen once in the first
-        # timed render at N=2; the renders themselves repeat to 1 %), a single one for the multi-second config 4
         reps = 1 if key == "config4_staircase" else 3
-        times = []
-        for _ in range(reps):
+        rec = {"scene": name, "width": w, "height": h, "spp": spp}
+        if world == 1:
+            dev.render(spp, seed=2, out=frame)  # warm-up at full size: allocates the wavefront buffers
+            times = []
+            for _ in range(reps):
+                dev.reset_stats()
+                img = dev.render(spp, seed=1, out=frame)
+                times.append(dev.stats()["last_render_ms"])
+            st = dev.stats()
+            ms = float(np.median(times))
+            rays = st["rays_closest"] + st["rays_shadow"]
+            rec.update({"ms": ms, "spp_per_s": spp / (ms * 1e-3), "mrays_per_s": rays / (ms * 1e-3) / 1e6,
+                        "rays_closest": int(st["rays_closest"]), "rays_shadow": int(st["rays_shadow"]),
+                        "kernel_launches": int(st["kernel_launches"]), "timed_renders_ms": [round(x, 3) for x in times],
+                        "path": "trt_render (one GPU)"})
+            rec.update(frame_hashes(img))
+        else:
+            # ---- round-1 path, config 3 only: one process per GPU, torch.distributed reduce over NCCL
+            if key == "config3_veach_mis":
+                render_on_gpus(dev, spp, seed=2, out=frame)
+                tt = []
+                for _ in range(reps):
+                    barrier()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    img = render_on_gpus(dev, spp, seed=1, out=frame)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    tt.append(e0.elapsed_time(e1))
+                t = torch.tensor(tt, dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                if rank == 0:
+                    rec["one_process_per_gpu"] = {"ms": float(np.median(t.tolist())), "spp_per_s": spp / (float(np.median(t.tolist())) * 1e-3),
+                                                  "reduce": "torch.distributed.reduce(SUM, f64) over NCCL", **frame_hashes(img)}
             barrier()
-            dev.reset_stats()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            img = render_on_gpus(dev, spp, seed=1, out=frame)
-            e1.record()
-            torch.cuda.synchronize()
-            times.append(e0.elapsed_time(e1))
-        if world > 1:  # every rank must pick the same repetition: take the per-repetition max over ranks first
-            tt = torch.tensor(times, dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            times = [float(x) for x in tt.tolist()]
-        ms = float(np.median(times))
-        st = dev.stats()
-        counts = torch.tensor([ms, float(st["rays_closest"]), float(st["rays_shadow"]), float(st["kernel_launches"])],
-                              dtype=torch.float64, device="cuda")
-        mx = counts.clone()
-        if world > 1:
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-        ms = float(mx[0].item())
-        rays = float(counts[1].item() + counts[2].item())
-        out[key] = {"scene": name, "width": w, "height": h, "spp": spp, "ms": ms, "spp_per_s": spp / (ms * 1e-3),
-                    "mrays_per_s": rays / (ms * 1e-3) / 1e6, "rays_closest": int(counts[1].item()),
-                    "rays_shadow": int(counts[2].item()), "kernel_launches": int(counts[3].item()),
-                    "image_mean": float(img.mean()) if img is not None else None, "timed_renders_ms": [round(x, 3) for x in times],
-                    "sharding": "samples [r*spp/N, (r+1)*spp/N) per rank, scene replicated, one NCCL reduce(sum, f64, W*H*3)"}
+            # ---- the product path: rank 0 drives all N GPUs through trt_render_multi; the other ranks keep off their GPUs
+            if rank == 0:
+                devs = [dev] + [dev.replicate(i) for i in range(world) if i != local]
+                for label, flags in (("nccl", 0), ("peer", trt.RENDER_PEER_REDUCE)):
+                    trt.render_multi(devs, spp, seed=2, flags=flags, out=frame)  # warm-up (communicators, peer mappings)
+                    times = []
+                    for _ in range(reps):
+                        for d in devs:
+                            d.reset_stats()
+                        img, rgb = trt.render_multi(devs, spp, seed=1, flags=flags, out=frame, want_rgb8=True)
+                        times.append(dev.stats()["last_render_ms"])
+                    ms = float(np.median(times))
+                    sts = [d.stats() for d in devs]
+                    rays = sum(s_["rays_closest"] + s_["rays_shadow"] for s_ in sts)
+                    r = {"ms": ms, "spp_per_s": spp / (ms * 1e-3), "mrays_per_s": rays / (ms * 1e-3) / 1e6,
+                         "timed_renders_ms": [round(x, 3) for x in times], **frame_hashes(img, rgb)}
+                    if label == "nccl":
+                        rec.update(r)
+                        rec.update({"rays_closest": int(sum(s_["rays_closest"] for s_ in sts)),
+                                    "rays_shadow": int(sum(s_["rays_shadow"] for s_ in sts)),
+                                    "kernel_launches": int(sum(s_["kernel_launches"] for s_ in sts)),
+                                    "path": "trt_render_multi: one process, %d GPUs, scene replicated device to device, samples "
+                                            "[i*spp/N, (i+1)*spp/N) per GPU, ncclCommInitAll + one ncclReduce(sum, f64, W*H*3), "
+                                            "resolve on GPU 0" % world})
+                    else:
+                        rec["peer_reduce"] = dict(r, path="same, with the library's own kernel: GPU 0 reads the peers' buffers "
+                                                          "over NVLink, sums in rank order and resolves in one pass")
+                for d in devs[1:]:
+                    d.close()
+                store.set("trt_render_done_" + key, "1")
+            else:
+                store.wait(["trt_render_done_" + key])
         dev.close()
         barrier()
-        if rank == 0 and world == 1 and not args.no_cpu and key == "config3_veach_mis":
-            out[key]["cpu_reference"] = cpu_reference_render(name, w, h, tmp)
+        if rank == 0 and world == 1 and not args.no_cpu:
+            if key == "config3_veach_mis":
+                rec["cpu_reference"] = cpu_reference_render(name, w, h, tmp, full=False)
+            elif key == "config1_cornell_shell":
+                rec["cpu_reference"] = cpu_reference_render(name, w, h, tmp, full=True, spp=spp)
+            if "spp_per_s_at_config" in rec.get("cpu_reference", {}):
+                rec["vs_cpu_reference"] = rec["spp_per_s"] / rec["cpu_reference"]["spp_per_s_at_config"]
+        out[key] = rec
+    return out
+
+
+def other_scene_measurements(args, tmp):
+    """The dominant kernel on the scenes where it is NOT served from L1: staircase (31 k triangles, 1.9 MB) and the
+    10 M-triangle stress mesh of BASELINE config 5 (590 MB of nodes + triangles: the one config whose scene exceeds the
+    126 MB L2).  4 Mi config-2 rays each, device-resident, CUDA events; each with the DRAM traffic ncu measured for the
+    same launch against the measured HBM peak."""
+    import torch
+
+    import tinyraytracing_b200 as trt
+    from tinyraytracing_b200 import scenes, workloads
+
+    out = {}
+    n = 4 << 20
+
+    def measure(host, key, label):
+        dev = trt.DeviceScene(host, 0)
+
+        def tracer(rays):
+            ids, t = dev.trace_closest(rays)
+            hp, pn = dev.hit_attributes(rays, ids, t)
+            return ids, hp, pn
+
+        rays = workloads.fixed_ray_batch(n, host.camera(), host.root_box(), tracer)
+        d_rays = torch.from_numpy(rays).cuda()
+        d_id = torch.empty(n, dtype=torch.int32, device="cuda")
+        d_t = torch.empty(n, dtype=torch.float32, device="cuda")
+        sp = torch.cuda.current_stream().cuda_stream
+        for _ in range(3):
+            dev.trace_closest_async(d_rays.data_ptr(), n, d_id.data_ptr(), d_t.data_ptr(), args.flags, sp)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            dev.trace_closest_async(d_rays.data_ptr(), n, d_id.data_ptr(), d_t.data_ptr(), args.flags, sp)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        st = dev.stats()
+        rec = {"what": label, "tris": int(host.n_tris), "ref_depth": int(st["ref_depth"]), "rays_per_launch": n, "ms_per_launch": ms,
+               "closest_hit_mrays": n / (ms * 1e-3) / 1e6, "hit_fraction": float((d_id >= 0).float().mean()),
+               "work_per_ray": dev.trace_counters(rays[:: max(1, n >> 19)]), "rays_strict": int(st["rays_strict"])}
+        roof = issue_roofline(key, n, ms, None)
+        if roof:
+            rec["roofline"] = roof
+        dev.close()
+        return rec
+
+    f = scenes.materialize("staircase", os.path.join(tmp, "o_staircase"), width=1280, height=720)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    os.dup2(devnull, 1)
+    try:
+        host = trt.HostScene.load(f["xml"], f["obj"], f["mtl"], f["basedir"])
+    finally:
+        os.dup2(saved, 1)
+    out["staircase"] = measure(host, "staircase", "example-scenes-cg22/staircase (largest loadable cg22 scene)")
+    host.close()
+    if not args.no_stress:
+        t0 = time.perf_counter()
+        m = workloads.stress_mesh(2236)
+        cam = m["camera"]
+        host = trt.HostScene.from_arrays(m["v9"], m["mtl"], m["materials"], m["lights"], cam["eye"], cam["lookat"], cam["up"],
+                                         cam["fovy"], 3840, 2160, vn9=m["vn9"])
+        out["stress_10m"] = measure(host, "stress_10m", "BASELINE config 5: procedurally tessellated 10 M-triangle mesh (SURVEY §8d-5)")
+        out["stress_10m"]["host_build_s"] = round(host.build_seconds, 2)
+        out["stress_10m"]["setup_s"] = round(time.perf_counter() - t0, 1)
+        host.close()
     return out
 
 
@@ -565,18 +825,22 @@ def standin_measurements(args):
     return out
 
 
-def cpu_reference_render(name, w, h, tmp):
-    """The UNMODIFIED reference program (oracle/_ref/ref_cpu, stdin protocol of main.cpp:46-55) on the host cores,
-    on a bounded sample of the config: reduced resolution (same aspect) and spp = host cores so that its
-    `omp parallel for` over samples (main.cpp:79-81) has work for every core; wall clock around the process
-    (load + BVH build included, small for this scene); scaled linearly in pixel-samples."""
+def cpu_reference_render(name, w, h, tmp, full=False, spp=16):
+    """The UNMODIFIED reference program (oracle/_ref/ref_cpu, stdin protocol of main.cpp:46-55) on the host cores.
+    full: the config as it stands (config 1 is the reference's own CPU-runnable case).  Otherwise a bounded sample of the
+    config: reduced resolution (same aspect) and spp = host cores so that its `omp parallel for` over samples
+    (main.cpp:79-81) has work for every core, scaled linearly in pixel-samples.  Wall clock around the process (load +
+    BVH build included, small for these scenes)."""
     from tinyraytracing_b200 import scenes
 
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_cpu")
     if not os.path.exists(exe):
         return {"unavailable": "oracle/_ref/ref_cpu not built"}
     cores = os.cpu_count() or 1
-    sw, sh, spp = w // 5, h // 5, max(8, min(cores, 50))
+    if full:
+        sw, sh = w, h
+    else:
+        sw, sh, spp = w // 5, h // 5, max(8, min(cores, 50))
     d = os.path.join(tmp, "cpu_ref_" + name)
     f = scenes.materialize(name, d, width=sw, height=sh)
     inp = "%s\n%s\n%s\n%s\n%d\n" % (f["basedir"], f["mtl"], f["xml"], f["obj"], spp)
@@ -586,7 +850,8 @@ def cpu_reference_render(name, w, h, tmp):
     if r.returncode != 0:
         return {"unavailable": "ref_cpu exited %d" % r.returncode}
     pxs = sw * sh * spp / dt
-    return {"kind": "reference", "cores": cores, "sample": "%dx%d, %d spp, %.1f s wall" % (sw, sh, spp, dt),
+    return {"kind": "reference", "cores": cores, "threads": min(50, spp),
+            "sample": "%dx%d, %d spp, %.1f s wall%s" % (sw, sh, spp, dt, " (the whole config)" if full else ""),
             "pixel_samples_per_s": pxs, "spp_per_s_at_config": pxs / (w * h)}
 
 
@@ -672,7 +937,8 @@ def main():
     ap.add_argument("--flags", type=int, default=0, help="TRT_TRACE_* traversal flags (0 = default layout)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--extra", action="store_true", help="also measure the other scenes and the render path")
-    ap.add_argument("--no-render", action="store_true", help="skip the config-3/4 render measurements")
+    ap.add_argument("--no-render", action="store_true", help="skip the config-1/3/4 render measurements and the other scenes")
+    ap.add_argument("--no-stress", action="store_true", help="skip the 10 M-triangle stress mesh (about 40 s of host-side build)")
     ap.add_argument("--config4", action="store_true", help="also render config 4 (staircase 1920x1080) when N != 8")
     ap.add_argument("--spp3", type=int, default=256, help="spp of config 3 (veach-mis 1280x720)")
     ap.add_argument("--spp4", type=int, default=1024, help="spp of config 4 (staircase 1920x1080)")

@@ -47,8 +47,14 @@ struct BatchRays
     const float *rays6;
     int32_t *out_id;
     float *out_t;
+    static constexpr bool kHasBound = false; // every ray searches the whole of [0.0005, INF]
     __device__ __forceinline__ unsigned int locate(unsigned int i) const { return i; }
-    __device__ __forceinline__ void load(unsigned int i, float3 &S, float3 &d) const { loadRay(rays6, i, S, d); }
+    __device__ __forceinline__ void load(unsigned int i, float3 &S, float3 &d, float &tmax) const
+    {
+        loadRay(rays6, i, S, d);
+        tmax = TRT_INF;
+    }
+    __device__ __forceinline__ bool bounded(unsigned int) const { return false; }
     __device__ __forceinline__ void store(unsigned int i, const Hit &h) const
     {
         if (out_id)

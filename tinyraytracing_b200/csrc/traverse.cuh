@@ -457,6 +457,13 @@ __device__ __forceinline__ void traceWide(const SceneView &sv, float3 S, float3 
 //     two more ballots per step cost more than the stragglers it removes, staircase 6.44 -> 5.96 Grays/s.)
 // Results are identical to traceWide: only the order in which a ray's own nodes are visited changes, and the
 // (t, key) order decides the winner (see the header comment).
+// ncu on the render walk (profiles/r02_walk_staircase.txt): 52 % of the stall samples are waits on loads, and the three
+// pop loops alone — a local-memory load, a compare, a branch, at 2-4 lanes while the rest of the warp waits — hold
+// 20 % of all samples.  Two remedies were built and measured in round 2, and both lost: mirroring the
+// top stack entry in registers so that a pop only STARTS the load of the entry below (staircase 6.38 -> 6.18 Grays/s,
+// k_shadow 58.2 -> 61.2 ms: two more live registers at the 56-register cap), and handing a nearest child that is a leaf
+// straight to the postponed-leaf slot instead of pushing and popping it back (6.38 -> 6.22: the six selects that shift
+// the sorted children run for every lane, the saved store + load only for a fifth of the visits).
 struct WalkState
 {
     float3 S, d, inv, nsi; // inv: 1/d (the culling reciprocal of a class-1 ray, see cullInv); nsi = -(S * inv)
@@ -465,6 +472,7 @@ struct WalkState
     int sp;
 };
 
+#define TRT_WALK_PUSH(st, stack, e) (stack[st.sp++] = (e))
 #define TRT_WALK_POP(st, stack)                                                                                      \
     do                                                                                                              \
     {                                                                                                               \
@@ -474,6 +482,12 @@ struct WalkState
             e__ = stack[--st.sp];                                                                                   \
         } while (entryT(e__) > st.hit.t);                                                                           \
         st.cur = entryLink(e__);                                                                                    \
+    } while (0)
+#define TRT_WALK_RESET(st, stack)                                                                                    \
+    do                                                                                                              \
+    {                                                                                                               \
+        stack[0] = packEntry(-1.f, TRT_LINK_EXIT);                                                                  \
+        st.sp = 1;                                                                                                  \
     } while (0)
 
 // One inner-node step of lane state `st` (st.cur >= 0 on entry).
@@ -486,11 +500,11 @@ __device__ __forceinline__ void walkNodeStep(const SceneView &sv, WalkState &st,
         return;
     }
     if (o.nh > 3)
-        stack[st.sp++] = packEntry(o.k3, o.l3);
+        TRT_WALK_PUSH(st, stack, packEntry(o.k3, o.l3));
     if (o.nh > 2)
-        stack[st.sp++] = packEntry(o.k2, o.l2);
+        TRT_WALK_PUSH(st, stack, packEntry(o.k2, o.l2));
     if (o.nh > 1)
-        stack[st.sp++] = packEntry(o.k1, o.l1);
+        TRT_WALK_PUSH(st, stack, packEntry(o.k1, o.l1));
     st.cur = o.l0;
 }
 
@@ -528,8 +542,11 @@ __device__ __forceinline__ void walkPoolInside(const SceneView &sv, const WalkSt
 }
 
 // RAYS: struct with  unsigned locate(unsigned i)  (ray index -> the 32-bit token the walker keeps while the ray is in
-// flight, below 2^31),  void load(token, float3 &S, float3 &d),  void store(token, const Hit &)  (hit.id = post-build
-// triangle index)  and  void storeFast(sv, token, const Hit &)  (hit.id = index in the fast layout's own order).
+// flight, below 2^31; below 2^29 apart from RAYS's own flag bit 30 when kHasBound),  void load(token, float3 &S,
+// float3 &d, float &tmax)  (tmax: initial search bound, TRT_INF for none),  bool bounded(token),  void store(token,
+// const Hit &)  (hit.id = post-build triangle index)  and  void storeFast(sv, token, const Hit &)  (hit.id = index in
+// the fast layout's own order).  A bounded ray that finds nothing within its bound is walked again without one, so the
+// result is the unbounded search's in every case (kHasBound = false compiles the second attempt out).
 // `counter` must be zero at launch; n = number of rays.  Every thread of the block must call this.
 // POOLED selects the leaf phase: false = every lane scans its own leaf (scanLeaf); true = the warp pools the
 // candidates that pass the plane test and deals their inside tests out one per lane (see below; measured in
@@ -541,7 +558,8 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
 {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int kRefillIdle = TRT_WALK_REFILL;
-    constexpr unsigned kPathGateBit = 0x80000000u;
+    constexpr unsigned kPathGateBit = 0x80000000u, kRetryBit = 0x20000000u;
+    constexpr unsigned kOwnBits = kPathGateBit | (RAYS::kHasBound ? kRetryBit : 0u);
     const int lane = threadIdx.x & 31;
     // per warp: pool of (triangle, t, owner lane) candidates awaiting their inside test, and each lane's best
     // (t bits << 32 | rank) so far
@@ -578,12 +596,12 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                 if (mine < n)
                 {
                     ray = rays.locate(mine);
-                    rays.load(ray, st.S, st.d);
-                    st.hit.t = TRT_INF, st.hit.id = -1, st.hit.key = 0xFFFFFFFFu;
+                    rays.load(ray, st.S, st.d, st.hit.t);
+                    st.hit.id = -1, st.hit.key = 0xFFFFFFFFu;
                     const int cls = sv.use_wide ? rayClass(sv, st.S, st.d) : 3;
                     if (cls >= 2 || (POOLED && cls == 1)) // (the pooled inside tests have only the leaf-box gate)
                     {
-                        // rare: the reference's own walk, finished on the spot
+                        // rare: the reference's own walk (it sets its own, unbounded, start state), finished on the spot
                         if (cls != 3)
                         {
                             atomicAdd(sv.strict_counter, 1ull);
@@ -605,8 +623,7 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                             st.inv = cullInv(sv, st.inv);
                         }
                         st.nsi = f3(-(st.S.x * st.inv.x), -(st.S.y * st.inv.y), -(st.S.z * st.inv.z));
-                        stack[0] = packEntry(-1.f, TRT_LINK_EXIT);
-                        st.sp = 1;
+                        TRT_WALK_RESET(st, stack);
                         st.cur = sv.wide_root;
                         st.leaf = TRT_LINK_EMPTY;
                         if (st.cur == TRT_LINK_EMPTY) // empty scene
@@ -710,16 +727,29 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
         // ---- finished rays
         if (live && st.cur == TRT_LINK_EXIT && st.leaf == TRT_LINK_EMPTY)
         {
-            if (POOLED)
+            if (RAYS::kHasBound && !POOLED && st.hit.id < 0 && !(ray & kRetryBit) && rays.bounded(ray & ~kOwnBits))
             {
-                const unsigned long long b = best[lane];
-                st.hit.t = __uint_as_float((unsigned int)(b >> 32));
-                st.hit.id = __ldg(sv.rank_tri + (unsigned int)b);
-                rays.store(ray & ~kPathGateBit, st.hit);
+                // nothing within the bound: the same ray once more, unbounded
+                ray |= kRetryBit;
+                st.hit.t = TRT_INF, st.hit.key = 0xFFFFFFFFu;
+                TRT_WALK_RESET(st, stack);
+                st.cur = sv.wide_root;
+                if (st.cur < 0) // (wide_root is never EMPTY here: the ray was admitted to the fast layout)
+                    st.leaf = st.cur, st.cur = TRT_LINK_EXIT;
             }
             else
-                rays.storeFast(sv, ray & ~kPathGateBit, st.hit);
-            ray = 0xffffffffu;
+            {
+                if (POOLED)
+                {
+                    const unsigned long long b = best[lane];
+                    st.hit.t = __uint_as_float((unsigned int)(b >> 32));
+                    st.hit.id = __ldg(sv.rank_tri + (unsigned int)b);
+                    rays.store(ray & ~kOwnBits, st.hit);
+                }
+                else
+                    rays.storeFast(sv, ray & ~kOwnBits, st.hit);
+                ray = 0xffffffffu;
+            }
         }
     }
 }

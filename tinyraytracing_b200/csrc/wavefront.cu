@@ -75,7 +75,7 @@ struct WfBuffers
     float4 *thr, *L, *weight;
     uint32_t *nee_mask;
     int32_t *queue[2];
-    float4 *sh_o, *sh_d; // sh_o.w = contribution index (slot*n_lights + light), sh_d.w = light material
+    float4 *sh_o, *sh_d; // sh_o.w = contribution index (slot*n_lights + light), sh_d.w = search bound (just beyond the light point)
     float4 *sh_contrib;  // [slot*n_lights + light]
     // [0],[1]: path queue sizes (ping-pong); [kPool]: ray-pool cursor of the persistent walker; [kDone]: CTAs of the
     // running k_walk that have finished; [kShadowCount + l]: shadow rays queued for light l (segment l of sh_o / sh_d
@@ -84,8 +84,13 @@ struct WfBuffers
     int32_t capacity; // paths per batch = length of one per-light shadow segment
 };
 constexpr int kPool = 2, kDone = 3, kShadowCount = 8, kNumCounters = 8 + 32;
-// walker tokens: bit 31 is the walker's own class-1 mark, bit 30 tells a shadow-queue entry from a path slot
+// walker tokens: bits 31 and 29 are the walker's own (class-1 mark, "second, unbounded attempt"), bit 30 tells a
+// shadow-queue entry from a path slot
 constexpr unsigned kShadowBit = 0x40000000u;
+constexpr unsigned kTokenLimit = 0x20000000u; // slots and shadow-queue entries stay below 2^29
+#ifndef TRT_SHADOW_BOUND
+#define TRT_SHADOW_BOUND 1
+#endif
 
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
                                               uint32_t out[4])
@@ -117,14 +122,20 @@ struct Rng
 
 __device__ __forceinline__ float3 xyz(float4 v) { return f3(v.x, v.y, v.z); }
 
-// IEEE x / c for a finite c > 0, bit for bit, without the division's slow path on a zero dividend: FCHK sends
-// 0 / c to a ~100-instruction subroutine (ncu, profiles/r01_render_shade_staircase.txt: 11 % of k_shade's warp
-// instructions were that subroutine, fed by Ks = 0 and by colours with a zero channel).  +-0 / c = +-0 = x.
+// x / c for a finite c > 0 without the division's slow path.  FCHK sends a zero, denormal or tiny dividend to a
+// ~100-instruction subroutine that runs with one or two lanes of the warp (ncu, profiles/r02_shade_staircase.txt: 9 % of
+// k_shade's warp instructions at 1.7 lanes, fed by Ks = 0, by colours with a zero channel and by the specular term
+// Ks (Ns+2) cos^Ns of a narrow lobe, which is denormal for ~1.5 % of the evaluations at Ns = 1000).
+//   x == +-0:      +-0 / c = +-0 = x, exactly;
+//   |x| < 1e-30:   x * (1/c) — within one ulp of the IEEE quotient of a quantity that is 1e-30 of any radiance the frame
+//                  can show (the one place where this kernel's radiance arithmetic is not the reference's operation,
+//                  DESIGN.md §6);
+//   otherwise the IEEE division, bit for bit.
 __device__ __forceinline__ float divByPositive(float x, float c)
 {
-    const bool zero = (x == 0.f);
-    const float q = (zero ? 1.0f : x) / c;
-    return zero ? x : q;
+    const bool tiny = fabsf(x) < 1.0e-30f;
+    const float q = (tiny ? 1.0f : x) / c;
+    return tiny ? x * q : q; // (tiny: q = 1/c; x = +-0 gives +-0)
 }
 __device__ __forceinline__ float3 divByPositive(float3 v, float c)
 {
@@ -168,8 +179,15 @@ __global__ void __launch_bounds__(kBlock) k_raygen(SceneView sv, WfBuffers wf, i
 // entry index in sh_o / sh_d = light * capacity + position; both below 2^30 by the batch-size check of renderAccumulate).
 struct WalkRays
 {
+    // A light-sample ray starts its search with the distance just beyond its light point as the bound (sh_d.w): the
+    // closest hit of the whole ray is what pathTracing.cpp:51-58 asks for, and whenever anything is hit up to the light
+    // point — normally the light's own triangle — that IS the closest hit, found without walking or stacking what lies
+    // behind the light.  Only if nothing at all is hit within the bound (a sample on a triangle edge that the inside
+    // test rejects) does the walker start the ray again without one.
+    static constexpr bool kHasBound = TRT_SHADOW_BOUND != 0;
     WfBuffers wf;
     const TriShade *tri_shade;
+    const DeviceLight *lights;
     int n_lights, qsel;
     unsigned int n_closest;
     __device__ __forceinline__ unsigned int locate(unsigned int i) const
@@ -187,17 +205,20 @@ struct WalkRays
         }
         return kShadowBit | ((unsigned int)l * (unsigned int)wf.capacity + i);
     }
-    __device__ __forceinline__ void load(unsigned int tok, float3 &S, float3 &d) const
+    __device__ __forceinline__ void load(unsigned int tok, float3 &S, float3 &d, float &tmax) const
     {
         const bool sh = (tok & kShadowBit) != 0;
         const unsigned int e = tok & ~kShadowBit;
         const float4 o = sh ? wf.sh_o[e] : wf.ray_o[e], dd = sh ? wf.sh_d[e] : wf.ray_d[e];
         S = xyz(o), d = xyz(dd);
+        tmax = (kHasBound && sh) ? dd.w : TRT_INF;
     }
-    // pathTracing.cpp:54-58: visible iff the closest hit's material is the light's material
+    __device__ __forceinline__ bool bounded(unsigned int tok) const { return kHasBound && (tok & kShadowBit) != 0; }
+    // pathTracing.cpp:54-58: visible iff the closest hit's material is the light's material (entry e lies in the queue
+    // segment of its light)
     __device__ __forceinline__ void finishShadow(unsigned int e, bool hit, int mtl) const
     {
-        const bool visible = hit && mtl == __float_as_int(wf.sh_d[e].w);
+        const bool visible = hit && mtl == lights[e / (unsigned int)wf.capacity].material;
         if (!visible)
             wf.sh_contrib[__float_as_int(wf.sh_o[e].w)] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -225,7 +246,8 @@ __device__ __forceinline__ void traceGridStride(const SceneView &sv, RAYS &rays,
     {
         const unsigned int token = rays.locate((unsigned int)i);
         float3 S, d;
-        rays.load(token, S, d);
+        float tmax; // these walks ignore the bound: the unbounded search gives the same closest hit
+        rays.load(token, S, d, tmax);
         Hit hit;
         if (MODE == 1)
             traceRefTopology<false>(sv, S, d, hit);
@@ -250,7 +272,7 @@ __global__ void __launch_bounds__(kBlock, TRT_WALK_CTAS) k_walk(SceneView sv, Wf
     if (what & 2)
         for (int l = 0; l < sv.n_lights; ++l)
             n_sh += (unsigned int)wf.counters[kShadowCount + l];
-    WalkRays r{wf, sv.tri_shade, sv.n_lights, qsel, (what & 1) ? (unsigned int)wf.counters[qsel] : 0u};
+    WalkRays r{wf, sv.tri_shade, sv.lights, sv.n_lights, qsel, (what & 1) ? (unsigned int)wf.counters[qsel] : 0u};
     const unsigned int n = r.n_closest + n_sh;
     if (MODE != 0)
         traceGridStride<MODE>(sv, r, n);
@@ -477,7 +499,16 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) k_shade(SceneVie
                     // the specular term of a diffuse material is (+0 * (Ns + 2)) * 0 / 2pi = +0 in every channel
                     float3 spec_term = f3(0.f, 0.f, 0.f);
                     if (!no_spec)
-                        spec_term = divByPositive((m_Ks * (m_Ns + 2.0f)) * (float)pow(cos_alpha, (double)m_Ns), 2.0f * kPI);
+                    {
+                        // cos^Ns below 2^-110 (a narrow lobe seen from outside it: most evaluations at Ns = 250..1000) is
+                        // taken as 0 without running the double-precision pow — a 300-instruction subroutine that ncu
+                        // shows at 4 lanes; what is dropped is below 1e-30 of the diffuse term it would be added to.
+                        // (cos_alpha = 0: log2 = -inf; Ns = 0: the product is NaN or 0 and the pow runs.)
+                        float pw = 0.f;
+                        if (!(m_Ns * __log2f((float)cos_alpha) < -110.f))
+                            pw = (float)pow(cos_alpha, (double)m_Ns);
+                        spec_term = divByPositive((m_Ks * (m_Ns + 2.0f)) * pw, 2.0f * kPI);
+                    }
                     const float3 brdf = divByPositive(Kd, kPI) + spec_term;
                     const float3 contrib = intensity * brdf;
                     const int cidx = slot * sv.n_lights + li;
@@ -492,7 +523,8 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) k_shade(SceneVie
                         at = g.shfl(at, 0);
                         const size_t e = (size_t)li * wf.capacity + at + g.thread_rank();
                         wf.sh_o[e] = xyzw(P, __int_as_float(cidx));
-                        wf.sh_d[e] = xyzw(wo, __int_as_float(lt.material));
+                        // the light point lies at |diff| along wo (a unit vector up to rounding): search up to 1.001 x that
+                        wf.sh_d[e] = xyzw(wo, sqrtf(len2) * 1.001f);
                     }
                     mask |= 1u << li;
                 }
@@ -574,12 +606,16 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) k_shade(SceneVie
   }
 }
 
+// accum[pixel] += L of the batch's samples, ONE AT A TIME in sample order: the running double sum then goes through the
+// same sequence of additions however the samples were split into batches (round 1 summed a batch first and added the
+// partial sum, which changed last bits with the batch size on large frames), and a render resumed from a checkpoint
+// continues the very sequence an uninterrupted one follows.
 __global__ void __launch_bounds__(256) k_deposit(WfBuffers wf, double *accum, int npix, int samples_in_batch, int n_lights)
 {
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= npix)
         return;
-    double r = 0, g = 0, b = 0;
+    double r = accum[(size_t)pix * 3 + 0], g = accum[(size_t)pix * 3 + 1], b = accum[(size_t)pix * 3 + 2];
     for (int s = 0; s < samples_in_batch; ++s)
     {
         const int slot = s * npix + pix;
@@ -589,9 +625,9 @@ __global__ void __launch_bounds__(256) k_deposit(WfBuffers wf, double *accum, in
             settleVertex(wf, n_lights, slot, pm, wf.thr[slot], L);
         r += (double)L.x, g += (double)L.y, b += (double)L.z;
     }
-    accum[(size_t)pix * 3 + 0] += r;
-    accum[(size_t)pix * 3 + 1] += g;
-    accum[(size_t)pix * 3 + 2] += b;
+    accum[(size_t)pix * 3 + 0] = r;
+    accum[(size_t)pix * 3 + 1] = g;
+    accum[(size_t)pix * 3 + 2] = b;
 }
 
 // ---- trt_shade: a wavefront that starts from caller-supplied hits instead of camera rays (pathtracing.h:14) ----
@@ -734,7 +770,7 @@ static long long batchTarget(trt_scene *s, int batch_paths, long long &max_paths
     const int nl1 = std::max(1, s->view.n_lights);
     long long target = batch_paths > 0 ? batch_paths : (32ll << 20);
     // walker tokens carry two flag bits, and slot * n_lights + light indexes the light-sample contributions
-    max_paths = (long long)(kShadowBit - 1) / nl1;
+    max_paths = (long long)(kTokenLimit - 1) / nl1;
     if (batch_paths <= 0)
     {
         size_t free_b = 0, total_b = 0;
@@ -882,7 +918,7 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
     int spb = (int)std::max(1ll, std::min((long long)total_samples, target / npix));
     if (npix * spb > max_paths)
     {
-        setLastError("batch too large for 30-bit ray tokens (paths x lights must stay below 2^30)");
+        setLastError("batch too large for 29-bit ray tokens (paths x lights must stay below 2^29)");
         return TRT_ERR_LIMIT;
     }
     int rc = ensureWavefront(s, (int)(npix * spb));

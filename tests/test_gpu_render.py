@@ -86,7 +86,9 @@ def test_render_agrees_with_reference_statistically(name, device_scenes):
     """Against the reference's own shade() (tests/golden/<scene>_render.npz, two independent 64-spp runs A1, A2
     made by tools/make_golden.py): the reference is only statistically reproducible, so this is the
     noise-floor test of SURVEY §8c-3 on radiance clipped at 4x the image mean (NEE 1/r^2 fireflies dominate the
-    raw RMSE): channel means within 5 % (+ the A1/A2 spread) and RMSE(GPU, A) <= 1.25 * RMSE(A1, A2)."""
+    raw RMSE): channel means within 2 % of the reference's (SURVEY §8c-3's figure; round 1 allowed 5 % plus the A1/A2
+    spread — measured deviations are <= 1 % on every scene for three seeds, the spread itself is 0.2-1.1 %) and
+    RMSE(GPU, A) <= 1.25 * RMSE(A1, A2)."""
     import os
 
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + "_render.npz"))
@@ -96,7 +98,7 @@ def test_render_agrees_with_reference_statistically(name, device_scenes):
     c1, c2, cg = (np.minimum(x, clip) for x in (a1, a2, img))
     m1, m2, mg = (x.mean(axis=(0, 1)) for x in (c1, c2, cg))
     ref_mean = 0.5 * (m1 + m2)
-    assert np.all(np.abs(mg - ref_mean) <= 0.05 * ref_mean + np.abs(m1 - m2)), (mg, m1, m2)
+    assert np.all(np.abs(mg - ref_mean) <= 0.02 * ref_mean), (mg, m1, m2)
     floor = np.sqrt(((c1 - c2) ** 2).mean())
     assert np.sqrt(((cg - c1) ** 2).mean()) <= 1.25 * floor
     assert np.sqrt(((cg - c2) ** 2).mean()) <= 1.25 * floor

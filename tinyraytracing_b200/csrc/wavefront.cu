@@ -28,6 +28,7 @@
 #include "barycentric.cuh"
 
 #include <algorithm>
+#include <cstring>
 #include <memory>
 #include <cooperative_groups.h>
 
@@ -38,12 +39,20 @@ namespace trt
 namespace
 {
 constexpr int kBlock = 128;
-// k_shade is bound by registers (112 unconstrained) and insensitive to its instruction count (ncu + A/B):
-// 64-thread CTAs with at least 9 resident per SM cap it at 96 registers (48 bytes of spills) = 5 warps per scheduler
-// instead of 4 — the register file is partitioned per scheduler, so 112 registers give 4 warps whatever the CTA size.
-// Measured against 128 threads / 112 registers (k_shade's own device time, TRT_RENDER_PROFILE): back 2.73 -> 2.66 ms,
-// veach-mis 22.4 -> 21.4 ms, staircase 32.2 -> 30.9 ms.
-constexpr int kShadeBlock = 64, kShadeMinBlocks = 9;
+// k_shade is a long dependent chain per warp (ncu, profiles/r02_shade_staircase.txt: issue-active 44 %, 0.75 eligible warps
+// per cycle): its throughput is resident warps / that latency, so registers are traded for warps.  64-thread CTAs with a
+// minimum of 14 resident per SM cap it at 72 registers (88 bytes of spills) = 7 warps per scheduler.  k_shade's own
+// device time on back / veach-mis / staircase (TRT_RENDER_PROFILE; 512x512x16, 1280x720x32, 1280x720x16):
+//   min. CTAs  9 (86 registers, 5 warps / scheduler, round 1's setting)   2.48 / 18.39 / 27.26 ms
+//             12 (80, no spills, 6)                                        2.43 / 16.54 / 25.30
+//             14 (72, 88 B of spills, 7)                                   2.42 / 15.75 / 24.62   <- shipped
+//             16 (64, 194 B, 8)                                            2.52 / 15.38 / 24.45
+//             18 (56, 200 B, 9)                                            2.60 / 15.10 / 24.21
+//             21 (40, 530 B, 12)                                           3.13 / 15.80 / 25.67
+#ifndef TRT_SHADE_MINBLOCKS
+#define TRT_SHADE_MINBLOCKS 14
+#endif
+constexpr int kShadeBlock = 64, kShadeMinBlocks = TRT_SHADE_MINBLOCKS;
 constexpr int kMaxLights = 32;
 constexpr float kPI = 3.1415926f; // pathtracing.h:11
 constexpr float kPRR = 0.8f;      // pathtracing.h:12
@@ -265,8 +274,14 @@ __device__ __forceinline__ void traceGridStride(const SceneView &sv, RAYS &rays,
 #ifndef TRT_WALK_CTAS
 #define TRT_WALK_CTAS 9
 #endif
+// snap (what & 4 only, may be null): a slot of page-locked HOST memory mapped into the device.  The last CTA copies the
+// counters there before it resets them — the queue length and shadow-ray counts the previous depth's k_shade left —
+// then the sequence number `seq`: the host learns how the batch is decaying by polling that word, with no copy and no
+// event between the kernels of the stream (round 1's per-depth cudaMemcpyAsync + event put a copy-engine round trip
+// on the critical path of every depth).
 template <int MODE>
-__global__ void __launch_bounds__(kBlock, TRT_WALK_CTAS) k_walk(SceneView sv, WfBuffers wf, int qsel, int what)
+__global__ void __launch_bounds__(kBlock, TRT_WALK_CTAS) k_walk(SceneView sv, WfBuffers wf, int qsel, int what, int32_t *snap,
+                                                                int32_t seq)
 {
     unsigned int n_sh = 0;
     if (what & 2)
@@ -289,6 +304,17 @@ __global__ void __launch_bounds__(kBlock, TRT_WALK_CTAS) k_walk(SceneView sv, Wf
     __syncthreads();
     if (s_last)
     {
+        if ((what & 4) && snap)
+        {
+            if (threadIdx.x < kNumCounters)
+            {
+                snap[threadIdx.x] = wf.counters[threadIdx.x];
+                __threadfence_system();
+            }
+            __syncthreads(); // (s_last is uniform over the CTA)
+            if (threadIdx.x == 0)
+                *reinterpret_cast<volatile int32_t *>(snap + kNumCounters) = seq;
+        }
         if (threadIdx.x == 0)
             wf.counters[kPool] = 0, wf.counters[kDone] = 0;
         if (what & 4)
@@ -688,9 +714,10 @@ struct Wavefront
     int capacity = 0; // paths
     int n_lights = 0;
     std::vector<void *> allocs;
-    static constexpr int kRing = 8;
-    int32_t *h_ring = nullptr; // pinned: kRing snapshots of the device counters
-    cudaEvent_t ring_ev[kRing] = {};
+    static constexpr int kRing = 8, kSlot = kNumCounters + 8; // a slot: the counters, then the sequence word
+    int32_t *h_ring = nullptr; // page-locked and mapped: kRing snapshots of the device counters, written by k_walk itself
+    int32_t *d_ring = nullptr; // the same memory as the device sees it
+    int32_t seq = 0;           // sequence number of the last snapshot asked for
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int blocks_walk = 1, blocks_shade = 1;
     std::vector<cudaEvent_t> prof_ev; // TRT_RENDER_PROFILE: four timestamps per iteration, grown on demand
@@ -700,9 +727,6 @@ struct Wavefront
             cudaFree(p);
         if (h_ring)
             cudaFreeHost(h_ring);
-        for (cudaEvent_t e : ring_ev)
-            if (e)
-                cudaEventDestroy(e);
         for (cudaEvent_t e : {ev0, ev1})
             if (e)
                 cudaEventDestroy(e);
@@ -749,9 +773,9 @@ static int ensureWavefront(trt_scene *s, int paths)
         return rc;
     }
     TRT_CUDA(cudaMemset(b.counters, 0, kNumCounters * 4));
-    TRT_CUDA(cudaMallocHost((void **)&w->h_ring, Wavefront::kRing * kNumCounters * 4));
-    for (cudaEvent_t &e : w->ring_ev)
-        TRT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    TRT_CUDA(cudaHostAlloc((void **)&w->h_ring, Wavefront::kRing * Wavefront::kSlot * 4, cudaHostAllocMapped));
+    std::memset(w->h_ring, 0, Wavefront::kRing * Wavefront::kSlot * 4);
+    TRT_CUDA(cudaHostGetDevicePointer((void **)&w->d_ring, w->h_ring, 0));
     TRT_CUDA(cudaEventCreate(&w->ev0));
     TRT_CUDA(cudaEventCreate(&w->ev1));
     TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w->blocks_walk, k_walk<0>, kBlock, 0));
@@ -819,23 +843,42 @@ static int runDepthLoop(trt_scene *s, cudaStream_t stream, int n_paths, int npix
         TRT_CUDA(cudaEventRecord(w->prof_ev[prof_used++], stream));
         return TRT_OK;
     };
-    auto walk = [&](int q, int what, long long rays_bound) {
+    // snapshot slot of iteration `it` (written by the k_walk of iteration it + 1) and the sequence number it will carry
+    const int32_t seq0 = w->seq;
+    auto slotOf = [&](int it) { return (size_t)(it % Wavefront::kRing) * Wavefront::kSlot; };
+    auto walk = [&](int q, int what, long long rays_bound, int publish_it) {
         // grids follow the queue: its length two iterations ago bounds it (queues only shrink)
         const long long need = std::max(1ll, (rays_bound + kBlock - 1) / kBlock);
+        int32_t *snap = (publish_it >= 0 && (what & 4)) ? w->d_ring + slotOf(publish_it) : nullptr;
+        const int32_t seq = seq0 + 1 + publish_it;
         if (mode == 1)
-            k_walk<1><<<(unsigned)std::min(full_plain, need), kBlock, 0, stream>>>(s->view, b, q, what);
+            k_walk<1><<<(unsigned)std::min(full_plain, need), kBlock, 0, stream>>>(s->view, b, q, what, snap, seq);
         else if (mode == 2)
-            k_walk<2><<<(unsigned)std::min(full_plain, need), kBlock, 0, stream>>>(s->view, b, q, what);
+            k_walk<2><<<(unsigned)std::min(full_plain, need), kBlock, 0, stream>>>(s->view, b, q, what, snap, seq);
         else
-            k_walk<0><<<(unsigned)std::min(full_walk, need), kBlock, 0, stream>>>(s->view, b, q, what);
+            k_walk<0><<<(unsigned)std::min(full_walk, need), kBlock, 0, stream>>>(s->view, b, q, what, snap, seq);
         s->stats.kernel_launches++;
     };
     int q = 0, consumed = 0;
     bool dead = false;
     long long live_bound = n_paths; // no queue from here on is longer
     auto consume = [&](int it) -> int { // counters as they stood after k_shade of iteration `it`
-        TRT_CUDA(cudaEventSynchronize(w->ring_ev[it % Wavefront::kRing]));
-        const int32_t *c = w->h_ring + (size_t)(it % Wavefront::kRing) * kNumCounters;
+        const volatile int32_t *c = w->h_ring + slotOf(it);
+        const int32_t want = seq0 + 1 + it;
+        for (unsigned spins = 0; c[kNumCounters] != want; ++spins)
+        {
+            if ((spins & 0x3ff) == 0x3ff)
+            {
+                // the stream has drained (or failed) and the word never came: report instead of spinning for ever
+                const cudaError_t e = cudaStreamQuery(stream);
+                if (e != cudaErrorNotReady && c[kNumCounters] != want)
+                {
+                    setLastError(std::string("wavefront: counter snapshot never arrived: ") +
+                                 (e == cudaSuccess ? "stream idle" : cudaGetErrorString(e)));
+                    return TRT_ERR_CUDA;
+                }
+            }
+        }
         const int next_live = c[(it & 1) ^ 1];
         uint64_t shadow = 0;
         for (int l = 0; l < nl; ++l)
@@ -859,28 +902,31 @@ static int runDepthLoop(trt_scene *s, cudaStream_t stream, int n_paths, int npix
             if ((rc = stamp()))
                 return rc;
             if (walk_closest)
-                walk(q, 1, live_bound);
+                walk(q, 1, live_bound, -1);
             if ((rc = stamp()))
                 return rc;
             if (depth > 0)
-                walk(q, 2 | 4, sh_bound);
+                walk(q, 2 | 4, sh_bound, depth - 1);
             if ((rc = stamp()))
                 return rc;
         }
-        else if (walk_closest || depth > 0)
-            walk(q, (walk_closest ? 1 : 0) | 2 | 4, live_bound + sh_bound);
+        else if (depth > 0)
+            walk(q, 1 | 2 | 4, live_bound + sh_bound, depth - 1);
+        else if (walk_closest)
+            walk(q, 1 | 4, live_bound, -1);
         const long long shade_grid = std::min(full_shade, std::max(1ll, (live_bound + kShadeBlock - 1) / kShadeBlock));
         k_shade<<<(unsigned)shade_grid, kShadeBlock, 0, stream>>>(s->view, b, q, depth, max_depth, sample0, seed, npix, pixel0);
         s->stats.kernel_launches++;
-        TRT_CUDA(cudaMemcpyAsync(w->h_ring + (size_t)(depth % Wavefront::kRing) * kNumCounters, b.counters,
-                                 kNumCounters * 4, cudaMemcpyDeviceToHost, stream));
-        TRT_CUDA(cudaEventRecord(w->ring_ev[depth % Wavefront::kRing], stream));
         if (profile && (rc = stamp()))
             return rc;
         q ^= 1;
         if (depth >= kLag && (rc = consume(consumed++)))
             return rc;
     }
+    // one more walk: it serves whatever light samples the last k_shade emitted and publishes that depth's counters
+    walk(q, 1 | 2 | 4, live_bound * (1 + nl), depth - 1);
+    w->seq = seq0 + depth;
+    TRT_CUDA(cudaGetLastError());
     // iterations launched after the batch died are no-ops on empty queues; drain their snapshots
     for (; consumed < depth; ++consumed)
         if ((rc = consume(consumed)))

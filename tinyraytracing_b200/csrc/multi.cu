@@ -13,7 +13,9 @@
 #include "scene_impl.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <map>
@@ -233,6 +235,10 @@ int renderMulti(trt_scene *const *scenes, int n, const trt_render_params &p, dou
     }
     TRT_CUDA(cudaSetDevice(s0->device));
     TRT_CUDA(cudaEventRecord(s0->ev[0], s0->stream));
+    const bool timing = getenv("TRT_MULTI_TIMING") != nullptr; // host-clock phases on stderr (diagnostics)
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
+    std::vector<double> t_done(n, 0.0);
     auto work = [&](int i) {
         trt_scene *s = scenes[i];
         trt_render_params q = p;
@@ -254,6 +260,7 @@ int renderMulti(trt_scene *const *scenes, int n, const trt_render_params &p, dou
             errs[i] = trt_last_error(); // thread-local: carried back to the caller's thread below
         else if ((e = cudaEventRecord(done[i], s->stream)) != cudaSuccess)
             rcs[i] = TRT_ERR_CUDA, errs[i] = cudaGetErrorString(e);
+        t_done[i] = since();
     };
     {
         std::vector<std::thread> threads;
@@ -312,6 +319,7 @@ int renderMulti(trt_scene *const *scenes, int n, const trt_render_params &p, dou
         s0->stats.kernel_launches++;
     }
     TRT_CUDA(cudaEventRecord(s0->ev[1], s0->stream));
+    const double t_reduce_enqueued = since();
     if (image_rgb)
         TRT_CUDA(cudaMemcpyAsync(image_rgb, s0->d_frame_image, count * sizeof(double), cudaMemcpyDeviceToHost, s0->stream));
     if (rgb8)
@@ -327,6 +335,14 @@ int renderMulti(trt_scene *const *scenes, int n, const trt_render_params &p, dou
     float ms = 0;
     TRT_CUDA(cudaEventElapsedTime(&ms, s0->ev[0], s0->ev[1]));
     s0->stats.last_render_ms = ms;
+    if (timing)
+    {
+        std::fprintf(stderr, "trt_render_multi[%s, %d GPUs]: renders done at", peer ? "peer" : "nccl", n);
+        for (int i = 0; i < n; ++i)
+            std::fprintf(stderr, " %.2f", t_done[i]);
+        std::fprintf(stderr, " ms; reduce + resolve enqueued at %.2f; all done at %.2f; device time %.2f ms\n", t_reduce_enqueued,
+                     since(), ms);
+    }
     cleanup();
     return TRT_OK;
 }

@@ -867,6 +867,9 @@ static int runDepthLoop(trt_scene *s, cudaStream_t stream, int n_paths, int npix
         const int32_t want = seq0 + 1 + it;
         for (unsigned spins = 0; c[kNumCounters] != want; ++spins)
         {
+#if defined(__x86_64__)
+            __builtin_ia32_pause(); // one host thread per GPU polls like this under trt_render_multi: be a quiet spinner
+#endif
             if ((spins & 0x3ff) == 0x3ff)
             {
                 // the stream has drained (or failed) and the word never came: report instead of spinning for ever

@@ -120,3 +120,12 @@ def test_inconsistent_descriptions_are_rejected_not_thrown(host_scenes):
     assert lib.trt_accum_save(None, None, 0, 1, 0, 0, b"/tmp/x") == -1
     assert lib.trt_accum_load(None, b"/tmp/x", None, None, None, None, None) == -1
     assert not lib.trt_accum_create(None)
+
+
+def test_integration_md_shows_the_compiled_bridge():
+    """INTEGRATION.md §2 prints integration/trt_bridge.{h,cpp} and main_gpu.sed: the text a maintainer reads is the text
+    `make -C oracle bridge` compiles (and tests/test_gpu_bridge.py runs), not a sketch beside it."""
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for name in ("trt_bridge.h", "trt_bridge.cpp", "main_gpu.sed"):
+        body = open(os.path.join(ROOT, "integration", name)).read()
+        assert body in md, name

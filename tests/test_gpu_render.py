@@ -135,3 +135,24 @@ def test_render_into_pinned_frame(device_scenes):
         dev.render(2, seed=3, out=np.empty((dev.height, dev.width, 3), np.float32))
     with pytest.raises(ValueError):
         dev.render(2, seed=3, out=np.empty((dev.height + 1, dev.width, 3), np.float64))
+
+
+@pytest.mark.parametrize("name", ("veach-mis", "staircase"))
+def test_early_stop_of_occluded_light_samples_does_not_change_the_frame(name, host_scenes):
+    """The walk may stop a light-sample ray at the first occluder it finds in front of the light's box (two k_walk
+    instantiations, chosen per scene; TRT_SHADOW_STOP overrides the choice at trt_scene_create): visibility is a yes / no
+    answer, so the frame must be bit-identical with and without."""
+    import os
+
+    import tinyraytracing_b200 as trt
+
+    frames = []
+    for flag in ("0", "1"):
+        os.environ["TRT_SHADOW_STOP"] = flag
+        try:
+            dev = trt.DeviceScene(host_scenes[name], 0)
+        finally:
+            del os.environ["TRT_SHADOW_STOP"]
+        frames.append(dev.render(6, seed=17))
+        dev.close()
+    assert np.array_equal(frames[0], frames[1])

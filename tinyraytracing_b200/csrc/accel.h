@@ -97,6 +97,10 @@ struct SceneView
     const uint32_t *fast_key, *fast_rank;
     const int32_t *fast_orig, *fast_leaf;
     const int32_t *fast_mtl; // material of each fast-layout triangle (the only thing a light-sample ray needs of its hit)
+    // 2 per light: the union of the fast layout's (padded) boxes of every triangle that carries the light's material.
+    // No triangle of that material can be hit before a ray enters this box — what lets an occluded light sample stop at
+    // the first occluder it finds in front of it (WalkRays::canStop)
+    const float4 *light_box;
     const float4 *ref_leaf_box; // 2 per reference leaf: (AA.xyz, -) (BB.xyz, -)
     const int32_t *ref_leaf_parent; // per reference leaf: (parent's inner index << 1) | right-child bit, -1 if the leaf is the root
     int32_t check_leaf_box;     // 0 only when the whole scene is ONE reference leaf (scanned without a box test)
@@ -137,6 +141,7 @@ struct AccelBuild
     std::vector<uint32_t> fast_key, fast_rank;
     std::vector<int32_t> fast_orig, fast_leaf;
     std::vector<float4> ref_leaf_box;
+    std::vector<float4> light_box; // 2 per light (lo, hi), see SceneView::light_box
     std::vector<int32_t> ref_leaf_parent;
     bool root_is_reference_leaf = false;
     float scene_scale = 0.f;

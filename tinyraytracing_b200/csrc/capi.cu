@@ -298,9 +298,14 @@ static int sceneCreate(const trt_scene_desc *desc, int device, trt_scene **out)
         (rc = upload(s.get(), ab.fast_orig.data(), ab.fast_orig.size(), &v.fast_orig)) ||
         (rc = upload(s.get(), ab.fast_leaf.data(), ab.fast_leaf.size(), &v.fast_leaf)) ||
         (rc = upload(s.get(), ab.ref_leaf_box.data(), ab.ref_leaf_box.size(), &v.ref_leaf_box)) ||
+        (rc = upload(s.get(), ab.light_box.data(), ab.light_box.size(), &v.light_box)) ||
         (rc = upload(s.get(), ab.ref_leaf_parent.data(), ab.ref_leaf_parent.size(), &v.ref_leaf_parent)))
         return rc;
     v.check_leaf_box = ab.root_is_reference_leaf ? 0 : 1;
+    {
+        const char *e = getenv("TRT_SHADOW_STOP");
+        s->shadow_stop = v.use_wide && (e ? atoi(e) != 0 : ab.fast_orig.size() >= 8192);
+    }
     v.strict_origin_limit = kStrictOriginFactor * ab.scene_scale;
     if ((rc = newStrictCounter(s.get())))
         return rc;
@@ -421,6 +426,7 @@ static int sceneReplicate(const trt_scene *src, int device, trt_scene **out)
     s->view = src->view;
     s->width = src->width, s->height = src->height;
     s->host_textures = src->host_textures;
+    s->shadow_stop = src->shadow_stop;
     s->stats = trt_stats{};
     s->stats.accel_nodes = src->stats.accel_nodes, s->stats.accel_leaves = src->stats.accel_leaves;
     s->stats.ref_depth = src->stats.ref_depth, s->stats.accel_slivers = src->stats.accel_slivers;

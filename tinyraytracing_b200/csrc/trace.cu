@@ -55,6 +55,7 @@ struct BatchRays
         tmax = TRT_INF;
     }
     __device__ __forceinline__ bool bounded(unsigned int) const { return false; }
+    __device__ __forceinline__ bool canStop(const SceneView &, unsigned int, const Hit &, float3, float3) const { return false; }
     __device__ __forceinline__ void store(unsigned int i, const Hit &h) const
     {
         if (out_id)

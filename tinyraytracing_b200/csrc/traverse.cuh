@@ -665,8 +665,11 @@ __device__ __forceinline__ void walkPersistent(const SceneView &sv, RAYS &rays, 
                 if (has)
                 {
                     const int lf = ~st.leaf;
+                    const int32_t before = st.hit.id;
                     scanLeaf<true>(sv, lf >> 3, (lf & 7) + 1, st.S, st.d, st.inv, st.hit, (ray & kPathGateBit) != 0);
-                    if (st.cur < 0 && st.cur != TRT_LINK_EXIT)
+                    if (RAYS::kHasBound && st.hit.id != before && rays.canStop(sv, ray & ~kOwnBits, st.hit, st.inv, st.nsi))
+                        st.cur = TRT_LINK_EXIT, st.leaf = TRT_LINK_EMPTY; // the answer is known (see WalkRays::canStop)
+                    else if (st.cur < 0 && st.cur != TRT_LINK_EXIT)
                     {
                         st.leaf = st.cur; // a second leaf was reached while the first was postponed
                         TRT_WALK_POP(st, stack);

@@ -128,6 +128,8 @@ void trt_host_free(void *p);
 #define TRT_TRACE_REFTOPO 4u     /* ordered + pruned walk of the reference binary topology          */
 #define TRT_TRACE_PLAIN 8u       /* fast layout, one thread per ray without the persistent ray pool  */
 #define TRT_TRACE_POOLED 16u     /* persistent walker with warp-pooled inside tests (experimental)   */
+#define TRT_TRACE_PERSISTENT 32u /* the warp-persistent walker even where the library would pick the plain kernel
+                                    (scenes of a few nodes); results are identical in every mode                   */
 
 /* rays6: n*(origin.xyz, direction.xyz) float32.  tri_id: post-build triangle index of the reference's
  * winner (tie rule of bvh.cpp:168-172,219), -1 on miss.  t: HitRecord::distance, TRT_INF on miss.

@@ -8,7 +8,7 @@ from conftest import SCENES, make_rays
 
 pytestmark = pytest.mark.gpu
 
-MODES = {"default": 0, "plain": trt.TRACE_PLAIN, "pooled": trt.TRACE_POOLED, "reftopo": trt.TRACE_REFTOPO, "exhaustive": trt.TRACE_EXHAUSTIVE}
+MODES = {"default": 0, "plain": trt.TRACE_PLAIN, "persistent": trt.TRACE_PERSISTENT, "pooled": trt.TRACE_POOLED, "reftopo": trt.TRACE_REFTOPO, "exhaustive": trt.TRACE_EXHAUSTIVE}
 
 
 @pytest.mark.parametrize("name", SCENES)

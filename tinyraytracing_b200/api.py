@@ -10,7 +10,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 INF = np.float32(114514.0)
-TRACE_DEVICE_PTRS, TRACE_EXHAUSTIVE, TRACE_REFTOPO, TRACE_PLAIN, TRACE_POOLED = 1, 2, 4, 8, 16
+TRACE_DEVICE_PTRS, TRACE_EXHAUSTIVE, TRACE_REFTOPO, TRACE_PLAIN, TRACE_POOLED, TRACE_PERSISTENT = 1, 2, 4, 8, 16, 32
 RENDER_REFTOPO = 1
 RENDER_PLAIN = 2
 RENDER_PROFILE = 4

@@ -305,6 +305,8 @@ static int sceneCreate(const trt_scene_desc *desc, int device, trt_scene **out)
     {
         const char *e = getenv("TRT_SHADOW_STOP");
         s->shadow_stop = v.use_wide && (e ? atoi(e) != 0 : ab.fast_orig.size() >= 8192);
+        e = getenv("TRT_CLOSEST_PLAIN");
+        s->closest_plain = v.use_wide && (e ? atoi(e) != 0 : ab.wide_nodes.size() <= 64);
     }
     v.strict_origin_limit = kStrictOriginFactor * ab.scene_scale;
     if ((rc = newStrictCounter(s.get())))
@@ -427,6 +429,7 @@ static int sceneReplicate(const trt_scene *src, int device, trt_scene **out)
     s->width = src->width, s->height = src->height;
     s->host_textures = src->host_textures;
     s->shadow_stop = src->shadow_stop;
+    s->closest_plain = src->closest_plain;
     s->stats = trt_stats{};
     s->stats.accel_nodes = src->stats.accel_nodes, s->stats.accel_leaves = src->stats.accel_leaves;
     s->stats.ref_depth = src->stats.ref_depth, s->stats.accel_slivers = src->stats.accel_slivers;

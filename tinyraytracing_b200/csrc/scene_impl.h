@@ -56,6 +56,7 @@ struct trt_scene
     size_t chunk_rays = 0;
     unsigned int *d_counter = nullptr; // ray-pool cursors of the persistent kernels: a ring, one slot per launch in flight
     unsigned int counter_slot = 0;
+    bool closest_plain = false; // fixed batches use the plain thread-per-ray kernel (tiny scenes: every ray is short, trace.cu)
     bool shadow_stop = false; // the wavefront walks with the early stop of occluded light samples (wavefront.cu: WalkRays)
     int persistent_blocks_per_sm = 1, pooled_blocks_per_sm = 1;
     trt::Wavefront *wf = nullptr;

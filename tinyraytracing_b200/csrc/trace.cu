@@ -144,7 +144,13 @@ int launchClosest(trt_scene *s, const float *d_rays6, size_t n, int32_t *d_id, f
         k_closest<1><<<grid, kTraceBlock, 0, stream>>>(s->view, d_rays6, n, d_id, d_t);
     else if (flags & TRT_TRACE_REFTOPO)
         k_closest<0><<<grid, kTraceBlock, 0, stream>>>(s->view, d_rays6, n, d_id, d_t);
-    else if ((flags & TRT_TRACE_PLAIN) || n > 0x7fffffffull) // the walker's ray tokens are 31-bit (top bit: class-1 mark)
+    // Which walker serves a fixed batch by default: on a scene of a few nodes (the 26-triangle Cornell shell: 7) every ray
+    // is two or three node visits long, nothing is left for the persistent walker's refill machinery to balance, and the
+    // plain thread-per-ray kernel is faster (back, 16 Mi rays: 16.6 against 16.0 Grays/s; 1 Mi rays: 14.5 against 12.9).
+    // From veach-mis (600 nodes) up the persistent walker wins or ties (15.2 against 13.9; staircase 6.6 = 6.7), and in
+    // the wavefront it wins everywhere (staircase render 90 against 106 ms).  TRT_TRACE_PERSISTENT forces it.
+    else if ((flags & TRT_TRACE_PLAIN) || (s->closest_plain && !(flags & (TRT_TRACE_POOLED | TRT_TRACE_PERSISTENT))) ||
+             n > 0x7fffffffull) // the walker's ray tokens are 31-bit (top bit: class-1 mark)
         k_closest<2><<<grid, kTraceBlock, 0, stream>>>(s->view, d_rays6, n, d_id, d_t);
     else
     {

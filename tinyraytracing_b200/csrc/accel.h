@@ -66,7 +66,8 @@ struct DeviceMaterial
 
 struct DeviceLight
 {
-    int32_t material, first_tri, n_tris, _pad;
+    int32_t material, first_tri, n_tris;
+    float pdf; // (float)(double(1) / total area) of pathTracing.cpp:62, the same for every sample of the light
 };
 
 struct DeviceTexture

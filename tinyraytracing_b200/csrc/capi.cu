@@ -376,7 +376,9 @@ static int sceneCreate(const trt_scene_desc *desc, int device, trt_scene **out)
         if (l.material < 0 || l.material >= desc->n_materials || l.first_tri < 0 || l.n_tris < 0 ||
             l.first_tri + l.n_tris > desc->n_light_tris)
             return fail(TRT_ERR_INVALID, "trt_scene_create: light out of range");
-        lights[i] = DeviceLight{l.material, l.first_tri, l.n_tris, 0};
+        if (l.n_tris >= (1 << 23))
+            return fail(TRT_ERR_LIMIT, "trt_scene_create: a light of 2^23 triangles or more");
+        lights[i] = DeviceLight{l.material, l.first_tri, l.n_tris, (float)(double(1) / desc->materials[l.material].area)};
     }
     if ((rc = upload(s.get(), lights.data(), lights.size(), &v.lights)))
         return rc;

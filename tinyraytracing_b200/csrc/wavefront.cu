@@ -411,6 +411,12 @@ __device__ __forceinline__ void settleVertex(const WfBuffers &wf, int n_lights, 
     L.x += T.x * Ldir.x, L.y += T.y * Ldir.y, L.z += T.z * Ldir.z;
 }
 
+// K3.  (Round 2 also built a three-phase form of this kernel — vertex records in shared memory, the light picks of
+// a CTA compacted into a task list, the picked (vertex, light) pairs dealt out to full warps — to lift the light loop
+// from 18 to ~30 lanes per instruction.  Bit-identical frames, and 5 % SLOWER (k_shade 24.1 -> 25.3 ms staircase, 15.5
+// -> 16.2 veach-mis): the kernel's time is load and dependency latency — ncu: 27 % of stall samples on loads, among them
+// the round trip of the shadow-queue atomic of every light iteration, 26 % on fixed-latency dependencies, 14 % on
+// instruction fetch — not the lanes its instructions serve.  DESIGN.md §10.)
 __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) k_shade(SceneView sv, WfBuffers wf, int qsel, int depth, int max_depth,
                                                   int sample0, uint64_t seed, int npix, int pixel0)
 {
@@ -492,6 +498,10 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) k_shade(SceneVie
                     Kd = f3((float)((double)px[2] / 255), (float)((double)px[1] / 255), (float)((double)px[0] / 255));
                 }
 
+                // the same for every light: the diffuse BRDF term Kd / PI (:67) and |pn| (:63)
+                const float3 Kd_pi = divByPositive(Kd, kPI);
+                const float pn_len = length3(pn);
+
                 // ---- direct illumination :33-75
                 for (int li = 0; li < sv.n_lights; ++li)
                 {
@@ -538,13 +548,13 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) k_shade(SceneVie
                     const float wo_pn = dot3(wo, pn);
                     if (!(wo_pn > 0.f)) // :60 — the sample cannot contribute: the shadow ray is not traced
                         continue;
-                    const DeviceMaterial lm = sv.materials[lt.material];
-                    const float pdf_light = (float)(double(1) / lm.area);
+                    const float3 radiance = sv.materials[lt.material].radiance;
+                    const float pdf_light = lt.pdf; // (float)(double(1) / area) of :62, computed once per light on the host
                     const float cos_theta_p = fabsf(dot3(wo, light_n));
-                    const float cos_theta = fabsf(wo_pn / length3(pn));
+                    const float cos_theta = fabsf(wo_pn / pn_len);
                     const float3 diff = light_p - P;
                     const float len2 = dot3(diff, diff);
-                    const float3 intensity = (((lm.radiance * cos_theta_p) * cos_theta) / len2) / pdf_light;
+                    const float3 intensity = (((radiance * cos_theta_p) * cos_theta) / len2) / pdf_light;
                     const float3 h = normalize3((wi + wo) * 0.5f);
                     const double cos_alpha = fmax((double)dot3(pn, h), 0.0);
                     // Ks == 0 (every diffuse material): Ks * (Ns+2) * pow(...) is +0 for any finite power, and the
@@ -563,7 +573,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) k_shade(SceneVie
                             pw = (float)pow(cos_alpha, (double)m_Ns);
                         spec_term = divByPositive((m_Ks * (m_Ns + 2.0f)) * pw, 2.0f * kPI);
                     }
-                    const float3 brdf = divByPositive(Kd, kPI) + spec_term;
+                    const float3 brdf = Kd_pi + spec_term;
                     const float3 contrib = intensity * brdf;
                     const int cidx = slot * sv.n_lights + li;
                     wf.sh_contrib[cidx] = xyzw(contrib, 0.f);

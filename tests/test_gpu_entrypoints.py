@@ -155,3 +155,44 @@ def test_strict_walk_counter(host_scenes, device_scenes):
     assert np.array_equal(ids, ex_ids) and np.array_equal(t.view(np.uint32), ex_t.view(np.uint32))
     dev.reset_stats()
     assert dev.stats()["rays_strict"] == 0
+
+
+def test_render_multi_edge_cases(host_scenes, device_scenes):
+    """Fewer samples than GPUs (one replica gets an empty range), a sample sub-range, rgb8 only, and a replica of a
+    replica: the fan-out must still give trt_render's frame."""
+    import ctypes as C
+
+    import tinyraytracing_b200 as trt
+
+    dev = device_scenes["back"]
+    a = trt.DeviceScene(host_scenes["back"], 0)
+    b = a.replicate(0)
+    c = b.replicate(0)
+    try:
+        one = dev.render(1, seed=4)
+        assert np.array_equal(trt.render_multi([a, b, c], 1, seed=4, flags=trt.RENDER_PEER_REDUCE), one)
+        assert b.stats()["paths"] == 0 or a.stats()["paths"] == 0 or c.stats()["paths"] == 0  # somebody had nothing to do
+        five = dev.render(5, seed=4)
+        got = trt.render_multi([a, b, c], 5, seed=4, flags=trt.RENDER_PEER_REDUCE)
+        assert np.allclose(got, five, rtol=1e-12, atol=0)
+        # image_rgb = NULL, rgb8 only
+        rgb = np.empty((a.height, a.width, 3), np.uint8)
+        handles = (C.c_void_p * 2)(a.h, b.h)
+        p = a.params(5, 0, 5, seed=4, flags=trt.RENDER_PEER_REDUCE)
+        assert a.lib.trt_render_multi(handles, 2, C.byref(p), None, rgb.ctypes.data) == 0
+        ref = np.clip(np.power(five, np.float64(np.float32(1.0) / np.float32(2.2))) * 255, 0, 255).astype(np.uint8)
+        assert np.abs(rgb.astype(int) - ref.astype(int)).max() <= 1
+        # bad sample range
+        p = a.params(5, 3, 2, seed=4)
+        assert a.lib.trt_render_multi(handles, 2, C.byref(p), None, rgb.ctypes.data) == -1
+    finally:
+        for d in (a, b, c):
+            d.close()
+
+
+def test_shade_of_nothing_and_of_misses(device_scenes):
+    dev = device_scenes["veach-mis"]
+    assert dev.shade(np.zeros((0, 6), np.float32), np.zeros(0, np.int32), np.zeros(0, np.float32)).shape == (0, 3)
+    rays = np.tile(np.array([0, 0, 0, 0, 1, 0], np.float32), (5, 1))
+    out = dev.shade(rays, np.full(5, -1, np.int32), np.full(5, 114514.0, np.float32))
+    assert np.all(out == 0)

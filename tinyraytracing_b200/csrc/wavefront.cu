@@ -133,6 +133,16 @@ struct Rng
 
 __device__ __forceinline__ float3 xyz(float4 v) { return f3(v.x, v.y, v.z); }
 
+// Programmatic dependent launch (sm_90+): the two kernels of a depth are launched with the programmatic-stream-
+// serialization attribute, so the next kernel's CTAs are set up and scheduled while the previous one drains, and wait
+// HERE, before they touch anything the previous kernel wrote, until it has completed and its writes are visible.  The
+// first statement of every kernel of the wavefront: a kernel launched the ordinary way falls through both.
+__device__ __forceinline__ void pdlEntry()
+{
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // x / c for a finite c > 0 without the division's slow path.  FCHK sends a zero, denormal or tiny dividend to a
 // ~100-instruction subroutine that runs with one or two lanes of the warp (ncu, profiles/r02_shade_staircase.txt: 9 % of
 // k_shade's warp instructions at 1.7 lanes, fed by Ks = 0, by colours with a zero channel and by the specular term
@@ -157,6 +167,7 @@ __device__ __forceinline__ float4 xyzw(float3 v, float w) { return make_float4(v
 // ------------------------------------------------------------------------------------------------ K1
 __global__ void __launch_bounds__(kBlock) k_raygen(SceneView sv, WfBuffers wf, int n_paths, int sample0, uint64_t seed)
 {
+    pdlEntry();
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (blockIdx.x == 0 && threadIdx.x < kNumCounters) // queue 0 = every slot; empty next queue, shadow segments, cursors
         wf.counters[threadIdx.x] = (threadIdx.x == 0) ? n_paths : 0;
@@ -311,6 +322,7 @@ template <int MODE, bool STOP>
 __global__ void __launch_bounds__(kBlock, TRT_WALK_CTAS) k_walk(SceneView sv, WfBuffers wf, int qsel, int what, int32_t *snap,
                                                                 int32_t seq)
 {
+    pdlEntry();
     unsigned int n_sh = 0;
     if (what & 2)
         for (int l = 0; l < sv.n_lights; ++l)
@@ -420,6 +432,7 @@ __device__ __forceinline__ void settleVertex(const WfBuffers &wf, int n_lights, 
 __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) k_shade(SceneView sv, WfBuffers wf, int qsel, int depth, int max_depth,
                                                   int sample0, uint64_t seed, int npix, int pixel0)
 {
+  pdlEntry();
   const int count = wf.counters[qsel];
   // warp-uniform grid-stride loop: the queue appends below are warp-collective
   for (int base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x)
@@ -676,6 +689,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) k_shade(SceneVie
 // continues the very sequence an uninterrupted one follows.
 __global__ void __launch_bounds__(256) k_deposit(WfBuffers wf, double *accum, int npix, int samples_in_batch, int n_lights)
 {
+    pdlEntry();
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= npix)
         return;
@@ -698,6 +712,7 @@ __global__ void __launch_bounds__(256) k_deposit(WfBuffers wf, double *accum, in
 __global__ void __launch_bounds__(kBlock) k_inject(WfBuffers wf, const float *__restrict__ rays6, const int32_t *__restrict__ id,
                                                    const float *__restrict__ t, int n)
 {
+    pdlEntry();
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (blockIdx.x == 0 && threadIdx.x < kNumCounters)
         wf.counters[threadIdx.x] = (threadIdx.x == 0) ? n : 0;
@@ -717,6 +732,7 @@ __global__ void __launch_bounds__(kBlock) k_inject(WfBuffers wf, const float *__
 
 __global__ void __launch_bounds__(kBlock) k_collect(WfBuffers wf, float *__restrict__ radiance3, int n, int n_lights)
 {
+    pdlEntry();
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n)
         return;
@@ -745,6 +761,27 @@ __global__ void __launch_bounds__(256) k_resolve(const double *accum, size_t n, 
     }
 }
 } // namespace
+
+// Launch with the programmatic-stream-serialization attribute (see pdlEntry).  TRT_PDL=0 launches the ordinary way.
+static bool usePdl()
+{
+    static const bool on = [] {
+        const char *e = getenv("TRT_PDL");
+        return !e || atoi(e) != 0;
+    }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+static void launchPdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t stream, bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = 0, cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...); // errors surface at the cudaGetLastError that follows
+}
 
 struct Wavefront
 {
@@ -872,6 +909,7 @@ static int runDepthLoop(trt_scene *s, cudaStream_t stream, int n_paths, int npix
     // whole extra pass of ~40 us warp iterations
     const long long full_shade = (long long)s->sm_count * std::max(1, w->blocks_shade);
     const bool profile = (flags & TRT_RENDER_PROFILE) != 0 && prof_ms;
+    const bool pdl = usePdl() && !profile; // (the profile's event records sit between the kernels)
     size_t prof_used = 0;
     int rc;
     auto stamp = [&]() -> int { // a timestamp on the stream between two launches
@@ -893,13 +931,13 @@ static int runDepthLoop(trt_scene *s, cudaStream_t stream, int n_paths, int npix
         int32_t *snap = (publish_it >= 0 && (what & 4)) ? w->d_ring + slotOf(publish_it) : nullptr;
         const int32_t seq = seq0 + 1 + publish_it;
         if (mode == 1)
-            k_walk<1, false><<<(unsigned)std::min(full_plain, need), kBlock, 0, stream>>>(s->view, b, q, what, snap, seq);
+            launchPdl(k_walk<1, false>, (unsigned)std::min(full_plain, need), kBlock, stream, pdl, s->view, b, q, what, snap, seq);
         else if (mode == 2)
-            k_walk<2, false><<<(unsigned)std::min(full_plain, need), kBlock, 0, stream>>>(s->view, b, q, what, snap, seq);
+            launchPdl(k_walk<2, false>, (unsigned)std::min(full_plain, need), kBlock, stream, pdl, s->view, b, q, what, snap, seq);
         else if (s->shadow_stop)
-            k_walk<0, true><<<(unsigned)std::min(full_walk, need), kBlock, 0, stream>>>(s->view, b, q, what, snap, seq);
+            launchPdl(k_walk<0, true>, (unsigned)std::min(full_walk, need), kBlock, stream, pdl, s->view, b, q, what, snap, seq);
         else
-            k_walk<0, false><<<(unsigned)std::min(full_walk, need), kBlock, 0, stream>>>(s->view, b, q, what, snap, seq);
+            launchPdl(k_walk<0, false>, (unsigned)std::min(full_walk, need), kBlock, stream, pdl, s->view, b, q, what, snap, seq);
         s->stats.kernel_launches++;
     };
     int q = 0, consumed = 0;
@@ -961,7 +999,7 @@ static int runDepthLoop(trt_scene *s, cudaStream_t stream, int n_paths, int npix
         else if (walk_closest)
             walk(q, 1 | 4, live_bound, -1);
         const long long shade_grid = std::min(full_shade, std::max(1ll, (live_bound + kShadeBlock - 1) / kShadeBlock));
-        k_shade<<<(unsigned)shade_grid, kShadeBlock, 0, stream>>>(s->view, b, q, depth, max_depth, sample0, seed, npix, pixel0);
+        launchPdl(k_shade, (unsigned)shade_grid, kShadeBlock, stream, pdl, s->view, b, q, depth, max_depth, sample0, seed, npix, pixel0);
         s->stats.kernel_launches++;
         if (profile && (rc = stamp()))
             return rc;
@@ -1035,7 +1073,8 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
         s->stats.rays_closest += (uint64_t)n_paths; // iteration 0 traces every path's camera ray
         if ((rc = runDepthLoop(s, stream, n_paths, (int)npix, 0, s0, p.seed, p.max_depth, p.flags, true, prof_ms)))
             return rc;
-        k_deposit<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(b, d_accum, (int)npix, ns, nl1);
+        launchPdl(k_deposit, (unsigned)((npix + 255) / 256), 256u, stream, usePdl() && !(p.flags & TRT_RENDER_PROFILE), b, d_accum,
+                  (int)npix, ns, nl1);
         s->stats.kernel_launches++;
         TRT_CUDA(cudaGetLastError());
     }

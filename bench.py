@@ -505,6 +505,10 @@ def run_gpu(args):
                                           "scene: the 2 kB scene is served from L1, so the ratio exceeds 1 by construction; the "
                                           "DRAM the kernel really moves is roofline.dram"}
         out["roofline"] = roof
+        if world > 1:
+            one = e2e_one_process(args, dev, lib, rays, n, rank, world, local, barrier)
+            if rank == 0:
+                out["e2e"]["one_process"] = one
         if not args.no_render:
             out["render"] = render_measurements(args, tmp, rank, world, local, barrier)
             if rank == 0 and world == 1:
@@ -584,6 +588,52 @@ def cpu_baseline(files, rays, gpu_ids=None, gpu_t=None, host=None):
                          "id_mismatches": int((~same).sum()),
                          "distance_bits_equal": bool(np.array_equal(t.view(np.uint32), np.asarray(ref_t).view(np.uint32))),
                          "against": "the unmodified reference traverseBVH" if kind == "reference" else "the oracle port"}
+    return out
+
+
+def e2e_one_process(args, dev, lib, rays, n, rank, world, local, barrier):
+    """The e2e leg once more with ONE process feeding all N GPUs (trt_trace_closest_multi: the batch shards by ray index
+    over replicas of the scene, one host thread per GPU) instead of N processes: N x 16 Mi rays in page-locked memory of
+    rank 0's process, the other ranks off their GPUs.  Says whether the host-side ceiling of `e2e.link` belongs to the
+    box or to the process layout."""
+    import torch.distributed as dist
+
+    import tinyraytracing_b200 as trt
+
+    barrier()
+    store = dist.distributed_c10d._get_default_store()
+    if rank != 0:
+        store.wait(["trt_e2e_one_process_done"])
+        return None
+    total = n * world
+    p_rays, p_id, p_t = lib.trt_host_alloc(total * 24), lib.trt_host_alloc(total * 4), lib.trt_host_alloc(total * 4)
+    out = None
+    try:
+        if p_rays and p_id and p_t:
+            for i in range(world):
+                C.memmove(p_rays + i * n * 24, rays.ctypes.data, n * 24)
+            devs = [dev] + [dev.replicate(i) for i in range(world) if i != local]
+            handles = (C.c_void_p * world)(*[d.h for d in devs])
+            call = lambda: lib.trt_trace_closest_multi(handles, world, p_rays, total, p_id, p_t, args.flags)
+            for _ in range(2):
+                assert call() == 0, lib.trt_last_error()
+            times = []
+            for _ in range(5):
+                t0 = time.perf_counter()
+                assert call() == 0, lib.trt_last_error()
+                times.append((time.perf_counter() - t0) * 1e3)
+            ms = float(np.median(times))
+            ids = np.ctypeslib.as_array(C.cast(p_id, C.POINTER(C.c_int32)), (total,))
+            same = all(np.array_equal(ids[i * n:(i + 1) * n], ids[:n]) for i in range(1, world))
+            out = {"value": total / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_call": ms, "rays_per_call": total,
+                   "shards_agree": bool(same), "what": "trt_trace_closest_multi: one process, %d GPUs, one host thread per GPU" % world}
+            for d in devs[1:]:
+                d.close()
+    finally:
+        for p in (p_rays, p_id, p_t):
+            if p:
+                lib.trt_host_free(p)
+        store.set("trt_e2e_one_process_done", "1")
     return out
 
 

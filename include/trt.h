@@ -143,6 +143,13 @@ int trt_trace_closest(trt_scene *scene, const float *rays6, size_t n, int32_t *t
 int trt_trace_closest_async(trt_scene *scene, const float *d_rays6, size_t n, int32_t *d_tri_id, float *d_t,
                             uint32_t flags, void *stream);
 
+/* The same for one host batch spread over several GPUs of the box: scenes[i] are replicas of one scene on different
+ * devices (trt_scene_replicate); GPU i traces rays [i*n/k, (i+1)*n/k) — the batch shards by ray index, there is no
+ * exchange step — each through its own chunked copy / kernel pipeline, driven by one host thread per GPU.  Host
+ * pointers only (TRT_TRACE_DEVICE_PTRS is refused).  Results are those of trt_trace_closest on any one of the scenes. */
+int trt_trace_closest_multi(trt_scene *const *scenes, int32_t k, const float *rays6, size_t n, int32_t *tri_id, float *t,
+                            uint32_t flags);
+
 /* Hit attributes the reference stores in HitRecord (bvh.h:7-15) for already-traced rays: hit point
  * S + d*t (bvh.cpp:191) and shading normal pn (bvh.cpp:223-224, least-squares barycentrics of
  * triangle.cpp:12-29 in double).  Host pointers. Either output may be NULL. */

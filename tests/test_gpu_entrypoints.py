@@ -196,3 +196,24 @@ def test_shade_of_nothing_and_of_misses(device_scenes):
     rays = np.tile(np.array([0, 0, 0, 0, 1, 0], np.float32), (5, 1))
     out = dev.shade(rays, np.full(5, -1, np.int32), np.full(5, 114514.0, np.float32))
     assert np.all(out == 0)
+
+
+def test_trace_closest_multi_shards_by_ray_index(host_scenes, oracle_scenes, device_scenes):
+    """One host batch spread over replicas (here three on one GPU; ragged shard sizes, a shard of zero rays): ids and
+    distance bits of the single-scene call, which are the oracle's."""
+    import tinyraytracing_b200 as trt
+
+    a = trt.DeviceScene(host_scenes["staircase"], 0)
+    reps = [a, a.replicate(0), a.replicate(0)]
+    try:
+        rays = make_rays(host_scenes["staircase"], oracle_scenes["staircase"], 100003, seed=12)
+        ids, t = trt.trace_closest_multi(reps, rays)
+        oid, ot = oracle_scenes["staircase"].trace(rays)
+        assert np.array_equal(ids, oid) and np.array_equal(t.view(np.uint32), ot.view(np.uint32))
+        ids2, t2 = trt.trace_closest_multi(reps, rays[:2])  # fewer rays than scenes
+        assert np.array_equal(ids2, oid[:2]) and np.array_equal(t2.view(np.uint32), ot[:2].view(np.uint32))
+        with pytest.raises(trt.TrtError):
+            trt.trace_closest_multi([a, a], rays[:10])
+    finally:
+        for d in reps:
+            d.close()

@@ -6,4 +6,4 @@ shared library and the C++ host mirror under csrc/.
 """
 from .api import (HostScene, DeviceScene, TrtError, RenderParams, load_library, library_path,  # noqa: F401
                   TRACE_EXHAUSTIVE, TRACE_REFTOPO, TRACE_PLAIN, TRACE_POOLED, TRACE_PERSISTENT, TRACE_DEVICE_PTRS, INF,
-                  RENDER_REFTOPO, RENDER_PLAIN, RENDER_PROFILE, RENDER_PEER_REDUCE, render_multi)
+                  RENDER_REFTOPO, RENDER_PLAIN, RENDER_PROFILE, RENDER_PEER_REDUCE, render_multi, trace_closest_multi)

@@ -84,7 +84,7 @@ class LayoutView(C.Structure):
 
 # every symbol include/trt.h and include/trt_host.h declare (tests check the library exports all of them)
 EXPORTS = ["trt_device_count", "trt_scene_create", "trt_scene_replicate", "trt_scene_destroy", "trt_host_alloc", "trt_host_free",
-           "trt_trace_closest", "trt_trace_closest_async", "trt_trace_counters", "trt_hit_attributes", "trt_render",
+           "trt_trace_closest", "trt_trace_closest_multi", "trt_trace_closest_async", "trt_trace_counters", "trt_hit_attributes", "trt_render",
            "trt_render_accumulate", "trt_resolve", "trt_render_multi", "trt_shade", "trt_accum_create", "trt_accum_destroy",
            "trt_accum_save", "trt_accum_load", "trt_layout_check", "trt_layout_build", "trt_layout_free", "trt_get_stats", "trt_reset_stats", "trt_last_error",
            "trt_version", "trt_host_scene_load", "trt_host_scene_from_arrays", "trt_host_scene_desc",
@@ -121,6 +121,7 @@ def load_library():
     L.trt_host_free.restype = None
     L.trt_trace_closest.argtypes = [vp, vp, sz, vp, vp, u32]
     L.trt_trace_closest_async.argtypes = [vp, vp, sz, vp, vp, u32, vp]
+    L.trt_trace_closest_multi.argtypes = [C.POINTER(vp), i32, vp, sz, vp, vp, u32]
     L.trt_hit_attributes.argtypes = [vp, vp, vp, vp, sz, vp, vp]
     L.trt_trace_counters.argtypes = [vp, vp, sz, vp]
     L.trt_render.argtypes = [vp, C.POINTER(RenderParams), vp]
@@ -315,6 +316,18 @@ class HostScene:
             self.close()
         except Exception:
             pass
+
+
+def trace_closest_multi(devs, rays, flags=0, out_id=None, out_t=None):
+    """trt_trace_closest_multi: one host batch sharded by ray index over the replicas `devs` (one per GPU)."""
+    rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+    n = len(rays)
+    ids = np.empty(n, np.int32) if out_id is None else out_id
+    t = np.empty(n, np.float32) if out_t is None else out_t
+    handles = (C.c_void_p * len(devs))(*[d.h for d in devs])
+    _check(devs[0].lib.trt_trace_closest_multi(handles, len(devs), rays.ctypes.data, n, ids.ctypes.data, t.ctypes.data, flags),
+           "trt_trace_closest_multi")
+    return ids, t
 
 
 def render_multi(devs, spp, seed=0, max_depth=0, flags=0, batch_paths=0, want_rgb8=False, out=None):

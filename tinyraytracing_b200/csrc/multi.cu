@@ -385,6 +385,50 @@ int trt_render_multi(trt_scene *const *scenes, int32_t n, const trt_render_param
     }
 }
 
+int trt_trace_closest_multi(trt_scene *const *scenes, int32_t k, const float *rays6, size_t n, int32_t *tri_id, float *t,
+                            uint32_t flags)
+{
+    if (!scenes || k < 1 || (!rays6 && n))
+        return fail(TRT_ERR_INVALID, "trt_trace_closest_multi: null argument / no scene");
+    if (flags & TRT_TRACE_DEVICE_PTRS)
+        return fail(TRT_ERR_INVALID, "trt_trace_closest_multi: host pointers only");
+    for (int i = 0; i < k; ++i)
+    {
+        if (!scenes[i])
+            return fail(TRT_ERR_INVALID, "trt_trace_closest_multi: null scene");
+        for (int j = 0; j < i; ++j)
+            if (scenes[j] == scenes[i])
+                return fail(TRT_ERR_INVALID, "trt_trace_closest_multi: the same scene handle twice");
+    }
+    std::vector<int> rcs(k, TRT_OK);
+    std::vector<std::string> errs(k);
+    auto work = [&](int i) {
+        const size_t lo = n * (size_t)i / (size_t)k, hi = n * (size_t)(i + 1) / (size_t)k; // contiguous shards that tile [0, n)
+        if (hi == lo)
+            return;
+        rcs[i] = trt_trace_closest(scenes[i], rays6 + lo * 6, hi - lo, tri_id ? tri_id + lo : nullptr, t ? t + lo : nullptr, flags);
+        if (rcs[i] != TRT_OK)
+            errs[i] = trt_last_error(); // thread-local: carried back to the caller's thread below
+    };
+    try
+    {
+        std::vector<std::thread> threads;
+        for (int i = 1; i < k; ++i)
+            threads.emplace_back(work, i);
+        work(0);
+        for (auto &th : threads)
+            th.join();
+    }
+    catch (const std::exception &e)
+    {
+        return fail(TRT_ERR_LIMIT, std::string("trt_trace_closest_multi: ") + e.what());
+    }
+    for (int i = 0; i < k; ++i)
+        if (rcs[i] != TRT_OK)
+            return fail(rcs[i], "trt_trace_closest_multi: scene " + std::to_string(i) + ": " + errs[i]);
+    return TRT_OK;
+}
+
 double *trt_accum_create(trt_scene *s)
 {
     if (!s)

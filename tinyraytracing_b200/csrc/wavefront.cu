@@ -783,6 +783,9 @@ static void launchPdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, c
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...); // errors surface at the cudaGetLastError that follows
 }
 
+// Path state of one batch in flight ("lane").  A scene has up to two: renderAccumulate keeps two batches going on two
+// streams, half a batch apart, so that the many short launches at the end of one batch (a depth costs ~30 us of kernel
+// latency however few paths are left) run while the other batch's full-size kernels fill the machine.
 struct Wavefront
 {
     WfBuffers buf{};
@@ -794,6 +797,8 @@ struct Wavefront
     int32_t *d_ring = nullptr; // the same memory as the device sees it
     int32_t seq = 0;           // sequence number of the last snapshot asked for
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t lane_stream = nullptr; // the second lane's own stream (the first lane works on the caller's)
+    cudaEvent_t ev_deposit = nullptr;   // recorded after this lane's latest k_deposit
     int blocks_walk = 1, blocks_shade = 1;
     std::vector<cudaEvent_t> prof_ev; // TRT_RENDER_PROFILE: four timestamps per iteration, grown on demand
     ~Wavefront()
@@ -802,9 +807,11 @@ struct Wavefront
             cudaFree(p);
         if (h_ring)
             cudaFreeHost(h_ring);
-        for (cudaEvent_t e : {ev0, ev1})
+        for (cudaEvent_t e : {ev0, ev1, ev_deposit})
             if (e)
                 cudaEventDestroy(e);
+        if (lane_stream)
+            cudaStreamDestroy(lane_stream);
         for (cudaEvent_t e : prof_ev)
             cudaEventDestroy(e);
     }
@@ -812,18 +819,22 @@ struct Wavefront
 
 void destroyWavefront(trt_scene *s)
 {
-    delete s->wf;
-    s->wf = nullptr;
+    for (Wavefront *&w : s->wf)
+    {
+        delete w;
+        w = nullptr;
+    }
 }
 
-// Path state for `paths` paths.  Built aside and published only when every allocation has succeeded, so that a
-// failed attempt (an explicit batch_paths beyond the free memory) leaves the scene without a wavefront and a retry
-// with a smaller batch starts clean.
-static int ensureWavefront(trt_scene *s, int paths)
+// Path state for `paths` paths in lane `lane`.  Built aside and published only when every allocation has succeeded, so
+// that a failed attempt (an explicit batch_paths beyond the free memory) leaves the scene without that wavefront and a
+// retry with a smaller batch starts clean.
+static int ensureWavefront(trt_scene *s, int lane, int paths)
 {
-    if (s->wf && s->wf->capacity >= paths)
+    if (s->wf[lane] && s->wf[lane]->capacity >= paths)
         return TRT_OK;
-    destroyWavefront(s);
+    delete s->wf[lane];
+    s->wf[lane] = nullptr;
     std::unique_ptr<Wavefront> w(new Wavefront());
     w->n_lights = std::max(1, s->view.n_lights);
     const size_t N = (size_t)paths, NL = N * w->n_lights;
@@ -853,20 +864,24 @@ static int ensureWavefront(trt_scene *s, int paths)
     TRT_CUDA(cudaHostGetDevicePointer((void **)&w->d_ring, w->h_ring, 0));
     TRT_CUDA(cudaEventCreate(&w->ev0));
     TRT_CUDA(cudaEventCreate(&w->ev1));
+    TRT_CUDA(cudaEventCreateWithFlags(&w->ev_deposit, cudaEventDisableTiming));
+    if (lane > 0)
+        TRT_CUDA(cudaStreamCreateWithFlags(&w->lane_stream, cudaStreamNonBlocking));
     if (s->shadow_stop)
         TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w->blocks_walk, k_walk<0, true>, kBlock, 0));
     else
         TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w->blocks_walk, k_walk<0, false>, kBlock, 0));
     TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w->blocks_shade, k_shade, kShadeBlock, 0));
     w->capacity = paths;
-    s->wf = w.release();
+    s->wf[lane] = w.release();
     return TRT_OK;
 }
 
-// Paths in flight per batch.  Path counts decay by 0.8 per depth and every depth costs two launches of at least one
-// wave whatever the queue length, so a batch should be large against that tail — but the tail is short now (round 1
-// paid five launches per depth and defaulted to 128 Mi paths = 52 GB with six lights for 2.6 % over 32 Mi).
-// Default: 32 Mi paths (13 GB with six lights), bounded by a third of the free memory; batch_paths asks for more.
+// Paths in flight (both lanes together).  Path counts decay by 0.8 per depth and every depth costs two launches of at
+// least one wave whatever the queue length, so a batch should be large against that tail — but the tail is short now
+// and hidden behind the other lane's batch (round 1 paid five launches per depth and defaulted to 128 Mi paths = 52 GB
+// with six lights for 2.6 % over 32 Mi).  Default: 32 Mi paths (13 GB with six lights), bounded by a third of the free
+// memory; batch_paths asks for more.
 static long long batchTarget(trt_scene *s, int batch_paths, long long &max_paths)
 {
     const int nl1 = std::max(1, s->view.n_lights);
@@ -879,7 +894,9 @@ static long long batchTarget(trt_scene *s, int batch_paths, long long &max_paths
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
         {
             const long long per_path = 100 + 48ll * nl1;
-            const long long have = (long long)(s->wf ? (size_t)s->wf->capacity * per_path : 0);
+            long long have = 0;
+            for (const Wavefront *w : s->wf)
+                have += (long long)(w ? (size_t)w->capacity * per_path : 0);
             target = std::min(target, std::max(1ll << 20, ((long long)free_b / 3 + have) / per_path));
         }
         target = std::min(target, max_paths);
@@ -887,32 +904,142 @@ static long long batchTarget(trt_scene *s, int batch_paths, long long &max_paths
     return target;
 }
 
-// The depth loop over the n_paths paths that k_raygen / k_inject have just set up in queue 0 (slot = index).
-// Stream keys of slot: pixel = pixel0 + slot % npix, sample = sample0 + slot / npix.  first_walk = false: the hits of depth 0
-// are already in hit_id / hit_t (trt_shade).  prof_ms (TRT_RENDER_PROFILE) += {closest-hit walk, shadow walk, shade}.
-static int runDepthLoop(trt_scene *s, cudaStream_t stream, int n_paths, int npix, int pixel0, int sample0, uint64_t seed,
-                        int max_depth, uint32_t flags, bool first_walk, double *prof_ms)
+// The depth loop over the n_paths paths that k_raygen / k_inject have just set up in queue 0 of a lane (slot = index),
+// as a state machine that never blocks: step() launches the next depth when the host may run that far ahead and takes
+// in the counter snapshots that have arrived, so that one host thread can keep two lanes going.
+// Stream keys of slot: pixel = pixel0 + slot % npix, sample = sample0 + slot / npix.  first_walk = false: the hits of
+// depth 0 are already in hit_id / hit_t (trt_shade).  prof_ms (TRT_RENDER_PROFILE) += {closest-hit walk, shadow walk, shade}.
+class DepthLoop
 {
-    Wavefront *w = s->wf;
-    const WfBuffers &b = w->buf;
-    const int nl = s->view.n_lights;
-    const int mode = (flags & TRT_RENDER_REFTOPO) ? 1 : ((flags & TRT_RENDER_PLAIN) ? 2 : 0);
+  public:
     // The host never waits for an iteration it has just launched: every kernel reads its queue length from device
     // memory, and the host looks at the counters of iteration it - kLag to learn when the batch has died out.  (At
-    // least one iteration is always launched after the one that emptied the queue: its k_walk serves the light
-    // samples of the last vertices.)
-    constexpr int kLag = 2;
-    static_assert(kLag >= 1, "the walk after the last k_shade serves its shadow rays");
-    const long long full_walk = (long long)s->sm_count * std::max(1, w->blocks_walk);
-    const long long full_plain = (long long)s->sm_count * 16;
-    // k_shade: exactly the resident CTAs (grid-stride loop inside): a second, partly filled wave of CTAs would cost a
-    // whole extra pass of ~40 us warp iterations
-    const long long full_shade = (long long)s->sm_count * std::max(1, w->blocks_shade);
-    const bool profile = (flags & TRT_RENDER_PROFILE) != 0 && prof_ms;
-    const bool pdl = usePdl() && !profile; // (the profile's event records sit between the kernels)
+    // least one walk is always launched after the k_shade that emptied the queue: it serves the light samples of the
+    // last vertices and publishes that depth's counters.)
+    static constexpr int kLag = 2;
+
+    void begin(trt_scene *scene, Wavefront *wave, cudaStream_t st, int paths, int npix_, int pixel0_, int sample0_, uint64_t seed_,
+               int max_depth_, uint32_t flags, bool first_walk_, double *prof_ms_)
+    {
+        s = scene, w = wave, stream = st, n_paths = paths, npix = npix_, pixel0 = pixel0_, sample0 = sample0_, seed = seed_;
+        max_depth = max_depth_, first_walk = first_walk_, prof_ms = prof_ms_;
+        mode = (flags & TRT_RENDER_REFTOPO) ? 1 : ((flags & TRT_RENDER_PLAIN) ? 2 : 0);
+        profile = (flags & TRT_RENDER_PROFILE) != 0 && prof_ms;
+        pdl = usePdl() && !profile; // (the profile's event records sit between the kernels)
+        nl = s->view.n_lights;
+        seq0 = w->seq;
+        q = 0, depth = 0, consumed = 0, dead = false, final_walk = false, prof_used = 0, live_bound = n_paths;
+        active = true;
+    }
+    bool finished() const { return active && final_walk && consumed == depth; }
+    bool idle() const { return !active; }
+    void release() { active = false; }
+    int depthReached() const { return depth; }
+    cudaStream_t streamOf() const { return stream; }
+
+    // > 0: made progress; 0: nothing to do right now; < 0: a trt_status
+    int step()
+    {
+        int progress = 0, rc;
+        while (awaited() && arrived(consumed)) // every snapshot that has come in, oldest first
+        {
+            consume(consumed++);
+            progress = 1;
+        }
+        if (!dead)
+        {
+            if (depth - consumed <= kLag) // the host runs at most kLag depths ahead of what it has seen
+            {
+                if ((rc = launchDepth()))
+                    return rc;
+                progress = 1;
+            }
+        }
+        else if (!final_walk)
+        {
+            // one more walk: it serves whatever light samples the last k_shade emitted and publishes its counters
+            walk(q, 1 | 2 | 4, 1, depth - 1);
+            w->seq = seq0 + depth;
+            final_walk = true;
+            TRT_CUDA(cudaGetLastError());
+            progress = 1;
+        }
+        return progress;
+    }
+
+    // the snapshot never came although the stream has drained (or failed): report instead of spinning for ever
+    int checkStalled()
+    {
+        const cudaError_t e = cudaStreamQuery(stream);
+        if (e != cudaErrorNotReady && awaited() && !arrived(consumed))
+        {
+            setLastError(std::string("wavefront: counter snapshot never arrived: ") +
+                         (e == cudaSuccess ? "stream idle" : cudaGetErrorString(e)));
+            return TRT_ERR_CUDA;
+        }
+        return TRT_OK;
+    }
+
+    // TRT_RENDER_PROFILE: four timestamps per iteration: closest-hit walk | shadow walk | shade
+    int finishProfile()
+    {
+        if (!profile)
+            return TRT_OK;
+        TRT_CUDA(cudaStreamSynchronize(stream));
+        const bool per_depth = getenv("TRT_RENDER_PROFILE_DEPTHS") != nullptr; // diagnostics: one stderr line per depth
+        for (size_t i = 0; i + 3 < prof_used; i += 4)
+        {
+            float d[3] = {0, 0, 0};
+            for (int k = 0; k < 3; ++k)
+            {
+                TRT_CUDA(cudaEventElapsedTime(&d[k], w->prof_ev[i + k], w->prof_ev[i + k + 1]));
+                prof_ms[k] += d[k];
+            }
+            if (per_depth)
+                std::fprintf(stderr, "depth %2zu: closest walk %.4f  shadow walk %.4f  shade %.4f ms\n", i / 4, d[0], d[1], d[2]);
+        }
+        return TRT_OK;
+    }
+
+  private:
+    trt_scene *s = nullptr;
+    Wavefront *w = nullptr;
+    cudaStream_t stream = nullptr;
+    int n_paths = 0, npix = 1, pixel0 = 0, sample0 = 0, max_depth = 0, mode = 0, nl = 0;
+    uint64_t seed = 0;
+    bool first_walk = true, profile = false, pdl = false, active = false;
+    double *prof_ms = nullptr;
+    int32_t seq0 = 0;
+    int q = 0, depth = 0, consumed = 0;
+    bool dead = false, final_walk = false;
+    long long live_bound = 0; // no queue from here on is longer
     size_t prof_used = 0;
-    int rc;
-    auto stamp = [&]() -> int { // a timestamp on the stream between two launches
+
+    size_t slotOf(int it) const { return (size_t)(it % Wavefront::kRing) * Wavefront::kSlot; }
+    // is the snapshot of depth `consumed` on its way?  A depth's counters are published by the walk of the NEXT depth, or
+    // by the final walk
+    bool awaited() const { return consumed < depth && (consumed < depth - 1 || final_walk); }
+    bool arrived(int it) const
+    {
+        const volatile int32_t *c = w->h_ring + slotOf(it);
+        return c[kNumCounters] == seq0 + 1 + it;
+    }
+    void consume(int it) // counters as they stood after k_shade of iteration `it`
+    {
+        const volatile int32_t *c = w->h_ring + slotOf(it);
+        const int next_live = c[(it & 1) ^ 1];
+        uint64_t shadow = 0;
+        for (int l = 0; l < nl; ++l)
+            shadow += (uint64_t)c[kShadowCount + l];
+        s->stats.rays_shadow += shadow;
+        s->stats.rays_closest += (uint64_t)next_live; // traced by iteration it + 1
+        if (!dead)
+            live_bound = next_live;
+        if (next_live == 0)
+            dead = true;
+    }
+    int stamp() // a timestamp on the stream between two launches
+    {
         if (prof_used == w->prof_ev.size())
         {
             cudaEvent_t e;
@@ -921,62 +1048,28 @@ static int runDepthLoop(trt_scene *s, cudaStream_t stream, int n_paths, int npix
         }
         TRT_CUDA(cudaEventRecord(w->prof_ev[prof_used++], stream));
         return TRT_OK;
-    };
-    // snapshot slot of iteration `it` (written by the k_walk of iteration it + 1) and the sequence number it will carry
-    const int32_t seq0 = w->seq;
-    auto slotOf = [&](int it) { return (size_t)(it % Wavefront::kRing) * Wavefront::kSlot; };
-    auto walk = [&](int q, int what, long long rays_bound, int publish_it) {
+    }
+    void walk(int qsel, int what, long long rays_bound, int publish_it)
+    {
+        const WfBuffers &b = w->buf;
+        const long long full_walk = (long long)s->sm_count * std::max(1, w->blocks_walk), full_plain = (long long)s->sm_count * 16;
         // grids follow the queue: its length two iterations ago bounds it (queues only shrink)
         const long long need = std::max(1ll, (rays_bound + kBlock - 1) / kBlock);
         int32_t *snap = (publish_it >= 0 && (what & 4)) ? w->d_ring + slotOf(publish_it) : nullptr;
         const int32_t seq = seq0 + 1 + publish_it;
         if (mode == 1)
-            launchPdl(k_walk<1, false>, (unsigned)std::min(full_plain, need), kBlock, stream, pdl, s->view, b, q, what, snap, seq);
+            launchPdl(k_walk<1, false>, (unsigned)std::min(full_plain, need), kBlock, stream, pdl, s->view, b, qsel, what, snap, seq);
         else if (mode == 2)
-            launchPdl(k_walk<2, false>, (unsigned)std::min(full_plain, need), kBlock, stream, pdl, s->view, b, q, what, snap, seq);
+            launchPdl(k_walk<2, false>, (unsigned)std::min(full_plain, need), kBlock, stream, pdl, s->view, b, qsel, what, snap, seq);
         else if (s->shadow_stop)
-            launchPdl(k_walk<0, true>, (unsigned)std::min(full_walk, need), kBlock, stream, pdl, s->view, b, q, what, snap, seq);
+            launchPdl(k_walk<0, true>, (unsigned)std::min(full_walk, need), kBlock, stream, pdl, s->view, b, qsel, what, snap, seq);
         else
-            launchPdl(k_walk<0, false>, (unsigned)std::min(full_walk, need), kBlock, stream, pdl, s->view, b, q, what, snap, seq);
+            launchPdl(k_walk<0, false>, (unsigned)std::min(full_walk, need), kBlock, stream, pdl, s->view, b, qsel, what, snap, seq);
         s->stats.kernel_launches++;
-    };
-    int q = 0, consumed = 0;
-    bool dead = false;
-    long long live_bound = n_paths; // no queue from here on is longer
-    auto consume = [&](int it) -> int { // counters as they stood after k_shade of iteration `it`
-        const volatile int32_t *c = w->h_ring + slotOf(it);
-        const int32_t want = seq0 + 1 + it;
-        for (unsigned spins = 0; c[kNumCounters] != want; ++spins)
-        {
-#if defined(__x86_64__)
-            __builtin_ia32_pause(); // one host thread per GPU polls like this under trt_render_multi: be a quiet spinner
-#endif
-            if ((spins & 0x3ff) == 0x3ff)
-            {
-                // the stream has drained (or failed) and the word never came: report instead of spinning for ever
-                const cudaError_t e = cudaStreamQuery(stream);
-                if (e != cudaErrorNotReady && c[kNumCounters] != want)
-                {
-                    setLastError(std::string("wavefront: counter snapshot never arrived: ") +
-                                 (e == cudaSuccess ? "stream idle" : cudaGetErrorString(e)));
-                    return TRT_ERR_CUDA;
-                }
-            }
-        }
-        const int next_live = c[(it & 1) ^ 1];
-        uint64_t shadow = 0;
-        for (int l = 0; l < nl; ++l)
-            shadow += (uint64_t)c[kShadowCount + l];
-        s->stats.rays_shadow += shadow;
-        s->stats.rays_closest += (uint64_t)next_live; // traced by iteration it + 1
-        live_bound = next_live;
-        if (next_live == 0)
-            dead = true;
-        return TRT_OK;
-    };
-    int depth = 0;
-    for (; !dead; ++depth)
+    }
+    int launchDepth()
     {
+        int rc;
         // the shadow rays of this walk come from the previous depth's vertices: at most n_lights per path of a
         // queue that was no longer than the bound either
         const long long sh_bound = depth > 0 ? live_bound * nl : 0;
@@ -998,41 +1091,50 @@ static int runDepthLoop(trt_scene *s, cudaStream_t stream, int n_paths, int npix
             walk(q, 1 | 2 | 4, live_bound + sh_bound, depth - 1);
         else if (walk_closest)
             walk(q, 1 | 4, live_bound, -1);
+        // k_shade: at most the resident CTAs (grid-stride loop inside): a second, partly filled wave of CTAs would cost a
+        // whole extra pass of ~40 us warp iterations
+        const long long full_shade = (long long)s->sm_count * std::max(1, w->blocks_shade);
         const long long shade_grid = std::min(full_shade, std::max(1ll, (live_bound + kShadeBlock - 1) / kShadeBlock));
-        launchPdl(k_shade, (unsigned)shade_grid, kShadeBlock, stream, pdl, s->view, b, q, depth, max_depth, sample0, seed, npix, pixel0);
+        launchPdl(k_shade, (unsigned)shade_grid, kShadeBlock, stream, pdl, s->view, w->buf, q, depth, max_depth, sample0, seed, npix, pixel0);
         s->stats.kernel_launches++;
         if (profile && (rc = stamp()))
             return rc;
         q ^= 1;
-        if (depth >= kLag && (rc = consume(consumed++)))
-            return rc;
+        ++depth;
+        TRT_CUDA(cudaGetLastError());
+        return TRT_OK;
     }
-    // one more walk: it serves whatever light samples the last k_shade emitted and publishes that depth's counters
-    walk(q, 1 | 2 | 4, live_bound * (1 + nl), depth - 1);
-    w->seq = seq0 + depth;
-    TRT_CUDA(cudaGetLastError());
-    // iterations launched after the batch died are no-ops on empty queues; drain their snapshots
-    for (; consumed < depth; ++consumed)
-        if ((rc = consume(consumed)))
-            return rc;
-    if (profile)
+};
+
+static inline void hostPause()
+{
+#if defined(__x86_64__)
+    __builtin_ia32_pause(); // one host thread per GPU polls under trt_render_multi: be a quiet spinner
+#endif
+}
+
+// drives one loop to its end (the single-lane users: profile renders, trt_shade)
+static int runToEnd(DepthLoop &loop)
+{
+    for (unsigned idle = 0; !loop.finished();)
     {
-        // four timestamps per iteration: closest-hit walk | shadow walk | shade + counter snapshot
-        TRT_CUDA(cudaStreamSynchronize(stream));
-        const bool per_depth = getenv("TRT_RENDER_PROFILE_DEPTHS") != nullptr; // diagnostics: one stderr line per depth
-        for (size_t i = 0; i + 3 < prof_used; i += 4)
+        const int r = loop.step();
+        if (r < 0)
+            return r;
+        if (r > 0)
         {
-            float d[3] = {0, 0, 0};
-            for (int k = 0; k < 3; ++k)
-            {
-                TRT_CUDA(cudaEventElapsedTime(&d[k], w->prof_ev[i + k], w->prof_ev[i + k + 1]));
-                prof_ms[k] += d[k];
-            }
-            if (per_depth)
-                std::fprintf(stderr, "depth %2zu: closest walk %.4f  shadow walk %.4f  shade %.4f ms\n", i / 4, d[0], d[1], d[2]);
+            idle = 0;
+            continue;
+        }
+        hostPause();
+        if ((++idle & 0x3ff) == 0)
+        {
+            const int rc = loop.checkStalled();
+            if (rc)
+                return rc;
         }
     }
-    return TRT_OK;
+    return loop.finishProfile();
 }
 
 int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, cudaStream_t stream)
@@ -1050,38 +1152,113 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
     const int total_samples = p.sample_end - p.sample_begin;
     if (total_samples <= 0)
         return TRT_OK;
-    int spb = (int)std::max(1ll, std::min((long long)total_samples, target / npix));
+    const bool profile = (p.flags & TRT_RENDER_PROFILE) != 0;
+    // Two lanes when the job is more than one batch of half the target: then the tail of every batch but the last runs
+    // under the other lane's bulk.  TRT_RENDER_LANES=1 keeps one (A/B runs); the frame is the same either way.
+    static const int max_lanes = [] {
+        const char *e = getenv("TRT_RENDER_LANES");
+        return e ? std::max(1, std::min(2, atoi(e))) : 2;
+    }();
+    int lanes = (profile || max_lanes < 2) ? 1 : 2;
+    int spb = (int)std::max(1ll, std::min((long long)total_samples, (target / lanes) / npix));
+    if (lanes == 2 && total_samples <= spb)
+        lanes = 1, spb = (int)std::max(1ll, std::min((long long)total_samples, target / npix));
     if (npix * spb > max_paths)
     {
         setLastError("batch too large for 29-bit ray tokens (paths x lights must stay below 2^29)");
         return TRT_ERR_LIMIT;
     }
-    int rc = ensureWavefront(s, (int)(npix * spb));
-    if (rc)
-        return rc;
-    Wavefront *w = s->wf;
-    const WfBuffers &b = w->buf;
-    double prof_ms[3] = {0, 0, 0};
-    TRT_CUDA(cudaEventRecord(w->ev0, stream));
-    for (int s0 = p.sample_begin; s0 < p.sample_end; s0 += spb)
-    {
-        const int ns = std::min(spb, p.sample_end - s0);
-        const int n_paths = (int)(npix * ns);
-        k_raygen<<<(unsigned)((n_paths + kBlock - 1) / kBlock), kBlock, 0, stream>>>(s->view, b, n_paths, s0, p.seed);
-        s->stats.kernel_launches++;
-        s->stats.paths += (uint64_t)n_paths;
-        s->stats.rays_closest += (uint64_t)n_paths; // iteration 0 traces every path's camera ray
-        if ((rc = runDepthLoop(s, stream, n_paths, (int)npix, 0, s0, p.seed, p.max_depth, p.flags, true, prof_ms)))
+    int rc;
+    for (int l = 0; l < lanes; ++l)
+        if ((rc = ensureWavefront(s, l, (int)(npix * spb))))
             return rc;
-        launchPdl(k_deposit, (unsigned)((npix + 255) / 256), 256u, stream, usePdl() && !(p.flags & TRT_RENDER_PROFILE), b, d_accum,
-                  (int)npix, ns, nl1);
-        s->stats.kernel_launches++;
-        TRT_CUDA(cudaGetLastError());
+    double prof_ms[3] = {0, 0, 0};
+    Wavefront *w0 = s->wf[0];
+    TRT_CUDA(cudaEventRecord(w0->ev0, stream));
+    cudaStream_t lane_stream[2] = {stream, lanes > 1 ? s->wf[1]->lane_stream : nullptr};
+    if (lanes > 1) // the second lane starts after whatever the caller has queued on `stream` (the zeroing of d_accum)
+        TRT_CUDA(cudaStreamWaitEvent(lane_stream[1], w0->ev0, 0));
+
+    // Batches are dealt to whichever lane is free; their deposits are issued in batch order (each waits for the previous
+    // one's event), so the accumulation buffer goes through the same sequence of additions as with one lane.
+    DepthLoop loop[2];
+    struct Batch
+    {
+        int s0, ns, index;
+    } cur[2] = {{0, 0, -1}, {0, 0, -1}};
+    const int kStagger = 6; // a lane starts a batch only once the other one's is this many depths in: half a batch apart
+    int next_s0 = p.sample_begin, next_index = 0, next_deposit = 0, last_deposit_lane = -1;
+    unsigned idle_spins = 0;
+    for (;;)
+    {
+        int progress = 0;
+        for (int l = 0; l < lanes; ++l)
+        {
+            DepthLoop &me = loop[l], &other = loop[l ^ 1];
+            if (me.idle())
+            {
+                if (next_s0 >= p.sample_end)
+                    continue;
+                if (lanes > 1 && !other.idle() && !other.finished() && other.depthReached() < kStagger)
+                    continue;
+                const int ns = std::min(spb, p.sample_end - next_s0);
+                const int n_paths = (int)(npix * ns);
+                Wavefront *w = s->wf[l];
+                k_raygen<<<(unsigned)((n_paths + kBlock - 1) / kBlock), kBlock, 0, lane_stream[l]>>>(s->view, w->buf, n_paths, next_s0,
+                                                                                                   p.seed);
+                s->stats.kernel_launches++;
+                s->stats.paths += (uint64_t)n_paths;
+                s->stats.rays_closest += (uint64_t)n_paths; // iteration 0 traces every path's camera ray
+                me.begin(s, w, lane_stream[l], n_paths, (int)npix, 0, next_s0, p.seed, p.max_depth, p.flags, true, prof_ms);
+                cur[l] = {next_s0, ns, next_index++};
+                next_s0 += ns;
+                progress = 1;
+            }
+            else if (!me.finished())
+            {
+                const int r = me.step();
+                if (r < 0)
+                    return r;
+                progress |= r;
+            }
+            else if (cur[l].index == next_deposit)
+            {
+                if ((rc = me.finishProfile()))
+                    return rc;
+                if (last_deposit_lane >= 0 && last_deposit_lane != l)
+                    TRT_CUDA(cudaStreamWaitEvent(lane_stream[l], s->wf[last_deposit_lane]->ev_deposit, 0));
+                launchPdl(k_deposit, (unsigned)((npix + 255) / 256), 256u, lane_stream[l], usePdl() && !profile, s->wf[l]->buf, d_accum,
+                          (int)npix, cur[l].ns, nl1);
+                s->stats.kernel_launches++;
+                TRT_CUDA(cudaGetLastError());
+                TRT_CUDA(cudaEventRecord(s->wf[l]->ev_deposit, lane_stream[l]));
+                last_deposit_lane = l;
+                ++next_deposit;
+                me.release();
+                progress = 1;
+            }
+        }
+        if (next_s0 >= p.sample_end && loop[0].idle() && loop[1].idle())
+            break;
+        if (progress)
+        {
+            idle_spins = 0;
+            continue;
+        }
+        hostPause();
+        if ((++idle_spins & 0x3ff) == 0)
+            for (int l = 0; l < lanes; ++l)
+                if (!loop[l].idle() && (rc = loop[l].checkStalled()))
+                    return rc;
     }
-    TRT_CUDA(cudaEventRecord(w->ev1, stream));
+    if (last_deposit_lane == 1) // the caller's stream ends after everything the second lane did
+        TRT_CUDA(cudaStreamWaitEvent(stream, s->wf[1]->ev_deposit, 0));
+    else if (lanes > 1 && last_deposit_lane == 0)
+        ; // lane 1's last deposit precedes lane 0's (deposits are chained), which is on `stream`
+    TRT_CUDA(cudaEventRecord(w0->ev1, stream));
     TRT_CUDA(cudaStreamSynchronize(stream));
     float ms = 0;
-    TRT_CUDA(cudaEventElapsedTime(&ms, w->ev0, w->ev1));
+    TRT_CUDA(cudaEventElapsedTime(&ms, w0->ev0, w0->ev1));
     s->stats.last_render_ms = ms;
     s->stats.ms_trace = prof_ms[0], s->stats.ms_shadow = prof_ms[1], s->stats.ms_shade = prof_ms[2];
     s->stats.ms_accumulate = 0.0; // folded into k_shade / k_deposit (settleVertex)
@@ -1103,10 +1280,11 @@ int shadeBatch(trt_scene *s, const float *d_rays6, const int32_t *d_id, const fl
     const int nl1 = std::max(1, s->view.n_lights);
     long long max_paths = 0;
     const long long target = std::min<long long>(batchTarget(s, 0, max_paths), (long long)n);
-    int rc = ensureWavefront(s, (int)target);
+    int rc = ensureWavefront(s, 0, (int)target);
     if (rc)
         return rc;
-    const WfBuffers &b = s->wf->buf;
+    Wavefront *w = s->wf[0];
+    const WfBuffers &b = w->buf;
     if (n > 0x7fffffffull)
     {
         setLastError("trt_shade: more than 2^31 - 1 rays in one call");
@@ -1119,8 +1297,9 @@ int shadeBatch(trt_scene *s, const float *d_rays6, const int32_t *d_id, const fl
         s->stats.kernel_launches++;
         s->stats.paths += (uint64_t)m;
         // stream of ray i: pixel key = i = chunk offset + slot (npix = INT_MAX keeps slot % npix = slot, slot / npix = 0)
-        if ((rc = runDepthLoop(s, stream, m, 0x7fffffff, (int)off, p.sample, p.seed, p.max_depth,
-                               p.flags & ~TRT_RENDER_PROFILE, false, nullptr)))
+        DepthLoop loop;
+        loop.begin(s, w, stream, m, 0x7fffffff, (int)off, p.sample, p.seed, p.max_depth, p.flags & ~TRT_RENDER_PROFILE, false, nullptr);
+        if ((rc = runToEnd(loop)))
             return rc;
         k_collect<<<(unsigned)((m + kBlock - 1) / kBlock), kBlock, 0, stream>>>(b, d_radiance3 + off * 3, m, nl1);
         s->stats.kernel_launches++;

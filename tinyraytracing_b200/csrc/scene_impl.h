@@ -59,7 +59,7 @@ struct trt_scene
     bool closest_plain = false; // fixed batches use the plain thread-per-ray kernel (tiny scenes: every ray is short, trace.cu)
     bool shadow_stop = false; // the wavefront walks with the early stop of occluded light samples (wavefront.cu: WalkRays)
     int persistent_blocks_per_sm = 1, pooled_blocks_per_sm = 1;
-    trt::Wavefront *wf[2] = {nullptr, nullptr}; // path state of the (up to two) batches in flight, wavefront.cu
+    trt::Wavefront *wf = nullptr;
     // frame buffers of trt_resolve / trt_render, allocated on first use and kept: a cudaMalloc / cudaFree pair per
     // call synchronises the device and costs more than the resolve kernel itself on small frames
     double *d_frame_image = nullptr, *d_frame_accum = nullptr;

@@ -783,9 +783,7 @@ static void launchPdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, c
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...); // errors surface at the cudaGetLastError that follows
 }
 
-// Path state of one batch in flight ("lane").  A scene has up to two: renderAccumulate keeps two batches going on two
-// streams, half a batch apart, so that the many short launches at the end of one batch (a depth costs ~30 us of kernel
-// latency however few paths are left) run while the other batch's full-size kernels fill the machine.
+// Path state of the batch in flight.
 struct Wavefront
 {
     WfBuffers buf{};
@@ -797,8 +795,6 @@ struct Wavefront
     int32_t *d_ring = nullptr; // the same memory as the device sees it
     int32_t seq = 0;           // sequence number of the last snapshot asked for
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaStream_t lane_stream = nullptr; // the second lane's own stream (the first lane works on the caller's)
-    cudaEvent_t ev_deposit = nullptr;   // recorded after this lane's latest k_deposit
     int blocks_walk = 1, blocks_shade = 1;
     std::vector<cudaEvent_t> prof_ev; // TRT_RENDER_PROFILE: four timestamps per iteration, grown on demand
     ~Wavefront()
@@ -807,11 +803,9 @@ struct Wavefront
             cudaFree(p);
         if (h_ring)
             cudaFreeHost(h_ring);
-        for (cudaEvent_t e : {ev0, ev1, ev_deposit})
+        for (cudaEvent_t e : {ev0, ev1})
             if (e)
                 cudaEventDestroy(e);
-        if (lane_stream)
-            cudaStreamDestroy(lane_stream);
         for (cudaEvent_t e : prof_ev)
             cudaEventDestroy(e);
     }
@@ -819,22 +813,18 @@ struct Wavefront
 
 void destroyWavefront(trt_scene *s)
 {
-    for (Wavefront *&w : s->wf)
-    {
-        delete w;
-        w = nullptr;
-    }
+    delete s->wf;
+    s->wf = nullptr;
 }
 
-// Path state for `paths` paths in lane `lane`.  Built aside and published only when every allocation has succeeded, so
-// that a failed attempt (an explicit batch_paths beyond the free memory) leaves the scene without that wavefront and a
-// retry with a smaller batch starts clean.
-static int ensureWavefront(trt_scene *s, int lane, int paths)
+// Path state for `paths` paths.  Built aside and published only when every allocation has succeeded, so that a
+// failed attempt (an explicit batch_paths beyond the free memory) leaves the scene without a wavefront and a retry
+// with a smaller batch starts clean.
+static int ensureWavefront(trt_scene *s, int paths)
 {
-    if (s->wf[lane] && s->wf[lane]->capacity >= paths)
+    if (s->wf && s->wf->capacity >= paths)
         return TRT_OK;
-    delete s->wf[lane];
-    s->wf[lane] = nullptr;
+    destroyWavefront(s);
     std::unique_ptr<Wavefront> w(new Wavefront());
     w->n_lights = std::max(1, s->view.n_lights);
     const size_t N = (size_t)paths, NL = N * w->n_lights;
@@ -864,24 +854,22 @@ static int ensureWavefront(trt_scene *s, int lane, int paths)
     TRT_CUDA(cudaHostGetDevicePointer((void **)&w->d_ring, w->h_ring, 0));
     TRT_CUDA(cudaEventCreate(&w->ev0));
     TRT_CUDA(cudaEventCreate(&w->ev1));
-    TRT_CUDA(cudaEventCreateWithFlags(&w->ev_deposit, cudaEventDisableTiming));
-    if (lane > 0)
-        TRT_CUDA(cudaStreamCreateWithFlags(&w->lane_stream, cudaStreamNonBlocking));
     if (s->shadow_stop)
         TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w->blocks_walk, k_walk<0, true>, kBlock, 0));
     else
         TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w->blocks_walk, k_walk<0, false>, kBlock, 0));
     TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w->blocks_shade, k_shade, kShadeBlock, 0));
     w->capacity = paths;
-    s->wf[lane] = w.release();
+    s->wf = w.release();
     return TRT_OK;
 }
 
-// Paths in flight (both lanes together).  Path counts decay by 0.8 per depth and every depth costs two launches of at
-// least one wave whatever the queue length, so a batch should be large against that tail — but the tail is short now
-// and hidden behind the other lane's batch (round 1 paid five launches per depth and defaulted to 128 Mi paths = 52 GB
-// with six lights for 2.6 % over 32 Mi).  Default: 32 Mi paths (13 GB with six lights), bounded by a third of the free
-// memory; batch_paths asks for more.
+// Paths in flight per batch.  Path counts decay by 0.8 per depth and every depth costs two launches of at least one
+// wave whatever the queue length, so a batch should be large against that tail — but the tail is short now (round 1
+// paid five launches per depth and defaulted to 128 Mi paths = 52 GB with six lights for 2.6 % over 32 Mi; with two
+// launches per depth, keeping a second batch in flight on a second stream to cover the tails was measured at 0.5 % on
+// veach-mis 256 spp and 0.1 % on staircase 1080p 128 spp, and taken out again).  Default: 32 Mi paths (13 GB with six
+// lights), bounded by a third of the free memory; batch_paths asks for more.
 static long long batchTarget(trt_scene *s, int batch_paths, long long &max_paths)
 {
     const int nl1 = std::max(1, s->view.n_lights);
@@ -894,9 +882,7 @@ static long long batchTarget(trt_scene *s, int batch_paths, long long &max_paths
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
         {
             const long long per_path = 100 + 48ll * nl1;
-            long long have = 0;
-            for (const Wavefront *w : s->wf)
-                have += (long long)(w ? (size_t)w->capacity * per_path : 0);
+            const long long have = (long long)(s->wf ? (size_t)s->wf->capacity * per_path : 0);
             target = std::min(target, std::max(1ll << 20, ((long long)free_b / 3 + have) / per_path));
         }
         target = std::min(target, max_paths);
@@ -906,7 +892,7 @@ static long long batchTarget(trt_scene *s, int batch_paths, long long &max_paths
 
 // The depth loop over the n_paths paths that k_raygen / k_inject have just set up in queue 0 of a lane (slot = index),
 // as a state machine that never blocks: step() launches the next depth when the host may run that far ahead and takes
-// in the counter snapshots that have arrived, so that one host thread can keep two lanes going.
+// in the counter snapshots that have arrived (runToEnd drives it; a host that has other work can interleave it).
 // Stream keys of slot: pixel = pixel0 + slot % npix, sample = sample0 + slot / npix.  first_walk = false: the hits of
 // depth 0 are already in hit_id / hit_t (trt_shade).  prof_ms (TRT_RENDER_PROFILE) += {closest-hit walk, shadow walk, shade}.
 class DepthLoop
@@ -932,10 +918,6 @@ class DepthLoop
         active = true;
     }
     bool finished() const { return active && final_walk && consumed == depth; }
-    bool idle() const { return !active; }
-    void release() { active = false; }
-    int depthReached() const { return depth; }
-    cudaStream_t streamOf() const { return stream; }
 
     // > 0: made progress; 0: nothing to do right now; < 0: a trt_status
     int step()
@@ -1152,113 +1134,40 @@ int renderAccumulate(trt_scene *s, const trt_render_params &p, double *d_accum, 
     const int total_samples = p.sample_end - p.sample_begin;
     if (total_samples <= 0)
         return TRT_OK;
-    const bool profile = (p.flags & TRT_RENDER_PROFILE) != 0;
-    // Two lanes when the job is more than one batch of half the target: then the tail of every batch but the last runs
-    // under the other lane's bulk.  TRT_RENDER_LANES=1 keeps one (A/B runs); the frame is the same either way.
-    static const int max_lanes = [] {
-        const char *e = getenv("TRT_RENDER_LANES");
-        return e ? std::max(1, std::min(2, atoi(e))) : 2;
-    }();
-    int lanes = (profile || max_lanes < 2) ? 1 : 2;
-    int spb = (int)std::max(1ll, std::min((long long)total_samples, (target / lanes) / npix));
-    if (lanes == 2 && total_samples <= spb)
-        lanes = 1, spb = (int)std::max(1ll, std::min((long long)total_samples, target / npix));
+    const int spb = (int)std::max(1ll, std::min((long long)total_samples, target / npix));
     if (npix * spb > max_paths)
     {
         setLastError("batch too large for 29-bit ray tokens (paths x lights must stay below 2^29)");
         return TRT_ERR_LIMIT;
     }
-    int rc;
-    for (int l = 0; l < lanes; ++l)
-        if ((rc = ensureWavefront(s, l, (int)(npix * spb))))
-            return rc;
+    int rc = ensureWavefront(s, (int)(npix * spb));
+    if (rc)
+        return rc;
+    Wavefront *w = s->wf;
+    const WfBuffers &b = w->buf;
+    const bool pdl = usePdl() && !(p.flags & TRT_RENDER_PROFILE);
     double prof_ms[3] = {0, 0, 0};
-    Wavefront *w0 = s->wf[0];
-    TRT_CUDA(cudaEventRecord(w0->ev0, stream));
-    cudaStream_t lane_stream[2] = {stream, lanes > 1 ? s->wf[1]->lane_stream : nullptr};
-    if (lanes > 1) // the second lane starts after whatever the caller has queued on `stream` (the zeroing of d_accum)
-        TRT_CUDA(cudaStreamWaitEvent(lane_stream[1], w0->ev0, 0));
-
-    // Batches are dealt to whichever lane is free; their deposits are issued in batch order (each waits for the previous
-    // one's event), so the accumulation buffer goes through the same sequence of additions as with one lane.
-    DepthLoop loop[2];
-    struct Batch
+    TRT_CUDA(cudaEventRecord(w->ev0, stream));
+    for (int s0 = p.sample_begin; s0 < p.sample_end; s0 += spb)
     {
-        int s0, ns, index;
-    } cur[2] = {{0, 0, -1}, {0, 0, -1}};
-    const int kStagger = 6; // a lane starts a batch only once the other one's is this many depths in: half a batch apart
-    int next_s0 = p.sample_begin, next_index = 0, next_deposit = 0, last_deposit_lane = -1;
-    unsigned idle_spins = 0;
-    for (;;)
-    {
-        int progress = 0;
-        for (int l = 0; l < lanes; ++l)
-        {
-            DepthLoop &me = loop[l], &other = loop[l ^ 1];
-            if (me.idle())
-            {
-                if (next_s0 >= p.sample_end)
-                    continue;
-                if (lanes > 1 && !other.idle() && !other.finished() && other.depthReached() < kStagger)
-                    continue;
-                const int ns = std::min(spb, p.sample_end - next_s0);
-                const int n_paths = (int)(npix * ns);
-                Wavefront *w = s->wf[l];
-                k_raygen<<<(unsigned)((n_paths + kBlock - 1) / kBlock), kBlock, 0, lane_stream[l]>>>(s->view, w->buf, n_paths, next_s0,
-                                                                                                   p.seed);
-                s->stats.kernel_launches++;
-                s->stats.paths += (uint64_t)n_paths;
-                s->stats.rays_closest += (uint64_t)n_paths; // iteration 0 traces every path's camera ray
-                me.begin(s, w, lane_stream[l], n_paths, (int)npix, 0, next_s0, p.seed, p.max_depth, p.flags, true, prof_ms);
-                cur[l] = {next_s0, ns, next_index++};
-                next_s0 += ns;
-                progress = 1;
-            }
-            else if (!me.finished())
-            {
-                const int r = me.step();
-                if (r < 0)
-                    return r;
-                progress |= r;
-            }
-            else if (cur[l].index == next_deposit)
-            {
-                if ((rc = me.finishProfile()))
-                    return rc;
-                if (last_deposit_lane >= 0 && last_deposit_lane != l)
-                    TRT_CUDA(cudaStreamWaitEvent(lane_stream[l], s->wf[last_deposit_lane]->ev_deposit, 0));
-                launchPdl(k_deposit, (unsigned)((npix + 255) / 256), 256u, lane_stream[l], usePdl() && !profile, s->wf[l]->buf, d_accum,
-                          (int)npix, cur[l].ns, nl1);
-                s->stats.kernel_launches++;
-                TRT_CUDA(cudaGetLastError());
-                TRT_CUDA(cudaEventRecord(s->wf[l]->ev_deposit, lane_stream[l]));
-                last_deposit_lane = l;
-                ++next_deposit;
-                me.release();
-                progress = 1;
-            }
-        }
-        if (next_s0 >= p.sample_end && loop[0].idle() && loop[1].idle())
-            break;
-        if (progress)
-        {
-            idle_spins = 0;
-            continue;
-        }
-        hostPause();
-        if ((++idle_spins & 0x3ff) == 0)
-            for (int l = 0; l < lanes; ++l)
-                if (!loop[l].idle() && (rc = loop[l].checkStalled()))
-                    return rc;
+        const int ns = std::min(spb, p.sample_end - s0);
+        const int n_paths = (int)(npix * ns);
+        k_raygen<<<(unsigned)((n_paths + kBlock - 1) / kBlock), kBlock, 0, stream>>>(s->view, b, n_paths, s0, p.seed);
+        s->stats.kernel_launches++;
+        s->stats.paths += (uint64_t)n_paths;
+        s->stats.rays_closest += (uint64_t)n_paths; // iteration 0 traces every path's camera ray
+        DepthLoop loop;
+        loop.begin(s, w, stream, n_paths, (int)npix, 0, s0, p.seed, p.max_depth, p.flags, true, prof_ms);
+        if ((rc = runToEnd(loop)))
+            return rc;
+        launchPdl(k_deposit, (unsigned)((npix + 255) / 256), 256u, stream, pdl, b, d_accum, (int)npix, ns, nl1);
+        s->stats.kernel_launches++;
+        TRT_CUDA(cudaGetLastError());
     }
-    if (last_deposit_lane == 1) // the caller's stream ends after everything the second lane did
-        TRT_CUDA(cudaStreamWaitEvent(stream, s->wf[1]->ev_deposit, 0));
-    else if (lanes > 1 && last_deposit_lane == 0)
-        ; // lane 1's last deposit precedes lane 0's (deposits are chained), which is on `stream`
-    TRT_CUDA(cudaEventRecord(w0->ev1, stream));
+    TRT_CUDA(cudaEventRecord(w->ev1, stream));
     TRT_CUDA(cudaStreamSynchronize(stream));
     float ms = 0;
-    TRT_CUDA(cudaEventElapsedTime(&ms, w0->ev0, w0->ev1));
+    TRT_CUDA(cudaEventElapsedTime(&ms, w->ev0, w->ev1));
     s->stats.last_render_ms = ms;
     s->stats.ms_trace = prof_ms[0], s->stats.ms_shadow = prof_ms[1], s->stats.ms_shade = prof_ms[2];
     s->stats.ms_accumulate = 0.0; // folded into k_shade / k_deposit (settleVertex)
@@ -1280,10 +1189,10 @@ int shadeBatch(trt_scene *s, const float *d_rays6, const int32_t *d_id, const fl
     const int nl1 = std::max(1, s->view.n_lights);
     long long max_paths = 0;
     const long long target = std::min<long long>(batchTarget(s, 0, max_paths), (long long)n);
-    int rc = ensureWavefront(s, 0, (int)target);
+    int rc = ensureWavefront(s, (int)target);
     if (rc)
         return rc;
-    Wavefront *w = s->wf[0];
+    Wavefront *w = s->wf;
     const WfBuffers &b = w->buf;
     if (n > 0x7fffffffull)
     {

@@ -368,17 +368,25 @@ __global__ void __launch_bounds__(kBlock, TRT_WALK_CTAS) k_walk(SceneView sv, Wf
 }
 
 // ------------------------------------------------------------------------------------------------ K3
-// pathTracing.cpp:111-145
+// pathTracing.cpp:111-145.  The reference draws theta = asin(sqrt(u)) (diffuse) or acos(u^(1/(Ns+1))) (specular) and
+// then takes sin(theta) and cos(theta); here sin(asin(x)) is x, cos(acos(y)) is y and the other one is the square root
+// of one minus the square — the same values to within the 1-2 ulp by which any two double libms differ (the oracle's
+// glibc and CUDA's already do), without two of the kernel's four double-precision transcendental calls per bounce.
 __device__ __forceinline__ float3 sampleLobe(float3 direction, int ray_type, double Ns, double u_phi, double u_theta)
 {
     const double phi = u_phi * 2 * (double)kPI;
-    double theta;
+    double st, ct;
     if (ray_type == DIFFUSE)
-        theta = asin(sqrt(u_theta));
+    {
+        st = sqrt(u_theta);       // sin(asin(sqrt(u)))
+        ct = sqrt(1.0 - u_theta); // cos(asin(sqrt(u)))
+    }
     else
-        theta = acos(pow(u_theta, (double)1 / (Ns + 1)));
-    double st, ct, sp, cp;
-    sincos(theta, &st, &ct);
+    {
+        ct = pow(u_theta, (double)1 / (Ns + 1)); // cos(acos(.))
+        st = sqrt(fmax(1.0 - ct * ct, 0.0));     // sin(acos(.))
+    }
+    double sp, cp;
     sincos(phi, &sp, &cp);
     const float3 sample = f3((float)(st * cp), (float)ct, (float)(st * sp));
     float3 front;

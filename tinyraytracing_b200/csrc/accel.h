@@ -62,6 +62,9 @@ struct DeviceMaterial
     float Ns, Ni;
     int32_t is_emissive, texture;
     double area;
+    // lobe-pick probabilities of nextRay (pathTracing.cpp:191-192): |Kd| / (|Kd| + |Ks|) and |Ks| / (|Kd| + |Ks|) with the
+    // MTL's Kd, lengths in float, quotients in double — a function of the material alone, computed once on the host
+    double kd, ks;
 };
 
 struct DeviceLight

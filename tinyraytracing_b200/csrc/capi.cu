@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <memory>
+#include <cmath>
 #include <cstddef>
 #include <cstdlib>
 #include <cstring>
@@ -364,6 +365,14 @@ static int sceneCreate(const trt_scene_desc *desc, int device, trt_scene **out)
         mats[i].Ns = m.Ns, mats[i].Ni = m.Ni;
         mats[i].is_emissive = m.is_emissive, mats[i].texture = m.texture;
         mats[i].area = m.area;
+        {
+            // glm::length in float (products first, then left-to-right adds; this file is compiled un-fused), as the
+            // device computed it per vertex until round 2
+            const float kd2 = (m.Kd[0] * m.Kd[0] + m.Kd[1] * m.Kd[1]) + m.Kd[2] * m.Kd[2];
+            const float ks2 = (m.Ks[0] * m.Ks[0] + m.Ks[1] * m.Ks[1]) + m.Ks[2] * m.Ks[2];
+            const double Kd_len = (double)std::sqrt(kd2), Ks_len = (double)std::sqrt(ks2);
+            mats[i].kd = Kd_len / (Kd_len + Ks_len), mats[i].ks = Ks_len / (Kd_len + Ks_len);
+        }
     }
     if ((rc = upload(s.get(), mats.data(), mats.size(), &v.materials)))
         return rc;

@@ -118,6 +118,15 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
 }
 
+// ((hi << 21) | (lo >> 11)) * 2^-53, the 53-bit uniform of DESIGN.md §5, without the 64-bit integer-to-double conversion
+// (a multi-instruction sequence on the GPU): the upper 21 and the lower 32 bits of that integer convert exactly one by
+// one, their weighted sum is below 2^53 and therefore exact too, and so is the scaling — the same double, bit for bit.
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo)
+{
+    const uint32_t top = hi >> 11, low = (hi << 21) | (lo >> 11);
+    return fma((double)top, 4294967296.0, (double)low) * (1.0 / 9007199254740992.0);
+}
+
 struct Rng
 {
     uint32_t k0, k1, pixel, sample, depth;
@@ -126,8 +135,8 @@ struct Rng
     {
         uint32_t o[4];
         philox4x32_10(pixel, sample, depth, blk, k0, k1, o);
-        u[0] = (double)(((uint64_t)o[0] << 21) | (uint64_t)(o[1] >> 11)) * (1.0 / 9007199254740992.0);
-        u[1] = (double)(((uint64_t)o[2] << 21) | (uint64_t)(o[3] >> 11)) * (1.0 / 9007199254740992.0);
+        u[0] = u53(o[0], o[1]);
+        u[1] = u53(o[2], o[3]);
     }
 };
 
@@ -655,8 +664,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) k_shade(SceneVie
                     }
                     if (!decided)
                     {
-                        const double Kd_len = (double)length3(mp->Kd), Ks_len = (double)length3(m_Ks);
-                        const double kd = Kd_len / (Kd_len + Ks_len), ks = Ks_len / (Kd_len + Ks_len);
+                        const double kd = mp->kd, ks = mp->ks; // |Kd| / (|Kd| + |Ks|), |Ks| / (...), :191-192 (host, once)
                         double ul[2], ut[2];
                         rng.block(2, ul);
                         const double p = ul[0];

@@ -958,6 +958,37 @@ std::string checkLayout(const trt_scene_desc &desc, const AccelBuild &ab, trt_la
 
     // walk the tree: leaves tile [0, nf), every node is reached once, boxes nest and hold their triangles with the pad
     const float pad = 256.f * (std::nextafter(scale, INFINITY) - scale);
+
+    // light boxes (the early stop of occluded light samples rests on them): every triangle of the fast layout that
+    // carries a light's material lies inside that light's box, with the pad unless it is a needle under its reference
+    // leaf's box — the same containment its path of boxes has to offer
+    if (ab.light_box.size() != (size_t)2 * std::max(0, desc.n_lights))
+        bad("light_box does not hold one box per light");
+    else
+        for (size_t i = 0; i < nf; ++i)
+        {
+            const int32_t t = ab.fast_orig[i];
+            const float *v = desc.v + (size_t)t * 9;
+            const float *rb = leafBox[ab.fast_leaf[i]];
+            for (int l = 0; l < desc.n_lights; ++l)
+            {
+                if (desc.lights[l].material != desc.mtl[t])
+                    continue;
+                const float4 lo4 = ab.light_box[2 * l], hi4 = ab.light_box[2 * l + 1];
+                const float lo[3] = {lo4.x, lo4.y, lo4.z}, hi[3] = {hi4.x, hi4.y, hi4.z};
+                bool padded = true, refbox = true;
+                for (int a = 0; a < 3; ++a)
+                {
+                    const float vlo = std::fmin(v[a], std::fmin(v[3 + a], v[6 + a])), vhi = std::fmax(v[a], std::fmax(v[3 + a], v[6 + a]));
+                    padded = padded && lo[a] <= vlo - pad && hi[a] >= vhi + pad;
+                    refbox = refbox && lo[a] <= rb[a] && hi[a] >= rb[3 + a];
+                }
+                if (!(padded || refbox))
+                    bad("a light's box does not contain one of its material's triangles with the pad");
+            }
+        }
+    if (rep.violations)
+        return first;
     std::vector<int32_t> covered(nf, 0), visited(ab.wide_nodes.size(), 0);
     auto leafInside = [&](int32_t link, const float *lo, const float *hi) {
         const int first = (~link) >> 3, count = ((~link) & 7) + 1;

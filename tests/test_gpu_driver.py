@@ -61,3 +61,36 @@ def test_cpp_host_surface_selftest(name, scene_files):
     r = subprocess.run([exe, f["basedir"], f["mtl"], f["xml"], f["obj"]], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                        text=True, timeout=300)
     assert r.returncode == 0 and "host selftest ok" in r.stdout, r.stdout[-2000:]
+
+
+def _trt_main(f, spp, env_extra, outdir):
+    import cv2
+
+    os.makedirs(outdir, exist_ok=True)
+    for fn in os.listdir(f["basedir"]):
+        dst = os.path.join(outdir, fn)
+        if not os.path.exists(dst):
+            os.symlink(os.path.join(f["basedir"], fn), dst)
+    rel = lambda p: os.path.join(outdir, os.path.relpath(p, f["basedir"]))
+    inp = "%s\n%s\n%s\n%s\n%d\n" % (outdir, rel(f["mtl"]), rel(f["xml"]), rel(f["obj"]), spp)
+    exe = os.path.join(ROOT, "tinyraytracing_b200", "bin", "trt_main")
+    r = subprocess.run([exe], input=inp, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300,
+                       env=dict(os.environ, TRT_SEED="23", **env_extra))
+    assert r.returncode == 0, r.stdout[-600:] + r.stderr[-600:]
+    return cv2.imread(os.path.join(outdir, "image%d.png" % spp), cv2.IMREAD_COLOR), r.stdout
+
+
+def test_trt_main_multi_device_and_checkpoint(scene_files, tmp_path):
+    """The C++ driver's round-2 switches: TRT_DEVICES (here the same GPU twice with the library's peer reduce, which a
+    one-GPU box can run; the NCCL flavour on distinct GPUs is tests/test_gpu_entrypoints.py's) and TRT_CHECKPOINT
+    (rendered in steps, then resumed from the finished file) give the PNG of the plain run."""
+    f = scene_files["veach-mis"]
+    plain, _ = _trt_main(f, 7, {}, str(tmp_path / "plain"))
+    multi, out = _trt_main(f, 7, {"TRT_DEVICES": "0,0", "TRT_PEER_REDUCE": "1"}, str(tmp_path / "multi"))
+    assert "rendered on 2 GPUs (peer-memory reduce)" in out
+    assert np.array_equal(plain, multi)
+    ck = str(tmp_path / "ck")
+    step, out = _trt_main(f, 7, {"TRT_CHECKPOINT": os.path.join(ck, "frame.ckpt"), "TRT_CHECKPOINT_EVERY": "3"}, ck)
+    assert "7 of 7 samples rendered by this run" in out and np.array_equal(plain, step)
+    again, out = _trt_main(f, 7, {"TRT_CHECKPOINT": os.path.join(ck, "frame.ckpt"), "TRT_CHECKPOINT_EVERY": "3"}, ck)
+    assert "0 of 7 samples rendered by this run" in out and np.array_equal(plain, again)

@@ -71,6 +71,50 @@ int main(int argc, char **argv)
             sum += v;
         }
         CHECK(sum > 0.0);
+
+        // PathTracing::shade (pathtracing.h:17): batch and single-record forms agree, emitters return their radiance,
+        // a miss shades to black, the stream index changes the numbers of a non-emissive hit
+        {
+            std::vector<vec3> rad = shade(out, dev, 7, 0, 0);
+            CHECK(rad.size() == 2 && rad[1].x == 0.f && rad[1].y == 0.f && rad[1].z == 0.f);
+            CHECK(std::isfinite(rad[0].x) && rad[0].x >= 0.f && rad[0].y >= 0.f && rad[0].z >= 0.f);
+            vec3 one = shade(out[0], -centre.direction, dev, 7, 0, 0);
+            CHECK(std::memcmp(&one, &rad[0], sizeof one) == 0);
+            if (out[0].triangle.is_emissive)
+            {
+                const vec3 r = scene.materials[out[0].triangle.mtl_name].radiance;
+                CHECK(rad[0].x == r.x && rad[0].y == r.y && rad[0].z == r.z);
+            }
+        }
+
+        // the fan-out over GPUs (main.cpp:79-81's role) with a replica of the scene on the same device and the library's
+        // peer reduce: the frame of the single-GPU loop up to the order of two double partial sums
+        {
+            DeviceScene replica(dev, 0, true);
+            std::vector<DeviceScene *> devs = {&dev, &replica};
+            std::vector<double> m(n);
+            renderImage(devs, 3, m.data(), 5, 0, TRT_RENDER_PEER_REDUCE);
+            std::vector<double> s3(n);
+            renderImage(dev, 3, s3.data(), 5);
+            for (size_t i = 0; i < n; ++i)
+                CHECK(std::fabs(m[i] - s3[i]) <= 1e-12 * std::fabs(s3[i]));
+        }
+
+        // checkpointed render: 5 samples in steps of 2, then "resumed" from the finished checkpoint (0 samples left): both
+        // times the frame of the uninterrupted render, bit for bit; a checkpoint made with another seed does not apply
+        {
+            const std::string ckpt = std::string(argv[1]) + "/selftest.ckpt";
+            std::remove(ckpt.c_str());
+            std::vector<double> u(n), r1(n), r2(n);
+            renderImage(dev, 5, u.data(), 9);
+            // (the uninterrupted render deposits its one batch sample by sample: the same sequence of additions)
+            CHECK(renderImageCheckpointed(dev, 5, r1.data(), ckpt, 2, 9) == 5);
+            CHECK(std::memcmp(u.data(), r1.data(), n * sizeof(double)) == 0);
+            CHECK(renderImageCheckpointed(dev, 5, r2.data(), ckpt, 2, 9) == 0);
+            CHECK(std::memcmp(u.data(), r2.data(), n * sizeof(double)) == 0);
+            CHECK(renderImageCheckpointed(dev, 5, r2.data(), ckpt, 2, 10) == 5); // another seed: the checkpoint does not apply
+            std::remove(ckpt.c_str());
+        }
         freeBVH(root);
     }
     catch (const std::exception &e)

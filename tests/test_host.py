@@ -299,3 +299,30 @@ def test_optimal_collapse_keeps_the_invariants_and_never_costs_more(host_scenes,
         assert opt["sah_wide"] <= greedy["sah_wide"] * (1 + 1e-6)
         assert opt["wide_nodes"] <= greedy["wide_nodes"]
     monkeypatch.delenv("TRT_COLLAPSE", raising=False)
+
+
+@pytest.mark.parametrize("seed", (1, 2))
+def test_layout_with_interpenetrating_lights(seed):
+    """Several lights whose triangles are scattered among the occluders and each other (workloads.light_soup): the layout's
+    invariants hold — among them that every triangle of a light's material lies in that light's box, which the early stop
+    of occluded light samples rests on — and the CPU walk of the layout returns the oracle's ids and distances."""
+    from tinyraytracing_b200 import workloads
+
+    m = workloads.light_soup(seed)
+    cam = m["camera"]
+    h = trt.HostScene.from_arrays(m["v9"], m["mtl"], m["materials"], m["lights"], cam["eye"], cam["lookat"], cam["up"],
+                                  cam["fovy"], m["width"], m["height"], vn9=m["vn9"])
+    rep = h.layout_check()
+    assert rep["violations"] == 0 and rep["use_wide"] == 1
+    ps = dict(v=m["v9"], vn=m["vn9"], vt=np.zeros((len(m["v9"]), 6), np.float32), mtl=m["mtl"],
+              materials=[dict(m_, name=str(i)) for i, m_ in enumerate(m["materials"])], lights=m["lights"], textures=[],
+              eye=np.array(cam["eye"], np.float32), lookat=np.array(cam["lookat"], np.float32),
+              up=np.array(cam["up"], np.float32), fovy=np.float32(cam["fovy"]), width=m["width"], height=m["height"])
+    o = oraclelib.OracleScene(ps)
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    rays = np.concatenate([workloads.camera_rays(h.camera(), 3000, rng), workloads.box_rays(*h.root_box(), 6000, rng)])
+    ids, t, _ = oraclelib.walk_layout(h, rays)
+    oid, ot = o.trace(rays)
+    served = ids != -2
+    assert served.mean() > 0.99
+    assert np.array_equal(ids[served], oid[served]) and np.array_equal(t[served].view(np.uint32), ot[served].view(np.uint32))

@@ -113,3 +113,36 @@ def stress_mesh(nq, radius=3.0, center=(0.0, 3.0, 0.0), room=8.0):
     materials = [diffuse, diffuse, dict(Kd=(0, 0, 0), Ks=(0, 0, 0), Tr=(1, 1, 1), Ns=1.0, Ni=1.0)]
     camera = dict(eye=(0.0, 4.0, -R * 2.6), lookat=(0.0, 3.5, 0.0), up=(0.0, 1.0, 0.0), fovy=40.0)
     return dict(v9=v, vn9=vn, mtl=mtl, materials=materials, lights=[(2, (18.0, 18.0, 18.0))], camera=camera)
+
+
+def light_soup(seed, n_occ=300, n_light_tris=24, n_lights=3, width=48, height=32):
+    """A random triangle soup in which emitters and occluders interpenetrate: several lights whose triangles are
+    scattered among (and behind, in front of, inside the boxes of) the occluders and of each other — the worst case for
+    the shadow logic of the walk (search bound at the light point, early stop in front of the light's box)."""
+    rng = np.random.default_rng(seed)
+
+    def tris(n, spread, size):
+        c = rng.uniform(-spread, spread, (n, 1, 3))
+        return (c + rng.normal(size=(n, 3, 3)) * size).reshape(n, 9)
+
+    v = [tris(n_occ, 1.0, 0.18)]
+    mtl = [rng.integers(0, 2, n_occ)]
+    for l in range(n_lights):
+        v.append(tris(n_light_tris, 1.0, 0.12))
+        mtl.append(np.full(n_light_tris, 2 + l))
+    # a floor and a back wall so that most camera rays hit something
+    v.append(np.array([[-3, -1.5, -3, 3, -1.5, -3, 3, -1.5, 3], [-3, -1.5, -3, 3, -1.5, 3, -3, -1.5, 3],
+                       [-3, -1.5, 3, 3, -1.5, 3, 3, 3, 3], [-3, -1.5, 3, 3, 3, 3, -3, 3, 3]], np.float64))
+    mtl.append(np.zeros(4, np.int64))
+    v = np.concatenate(v).astype(np.float32)
+    mtl = np.concatenate(mtl).astype(np.int32)
+    e1, e2 = v[:, 3:6] - v[:, 0:3], v[:, 6:9] - v[:, 0:3]
+    nrm = np.cross(e1, e2)
+    nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-20)
+    vn = np.tile(nrm, (1, 3)).astype(np.float32)
+    materials = [dict(Kd=(0.7, 0.6, 0.5), Ks=(0, 0, 0), Tr=(1, 1, 1), Ns=1.0, Ni=1.0),
+                 dict(Kd=(0.2, 0.3, 0.4), Ks=(0.5, 0.5, 0.5), Tr=(1, 1, 1), Ns=60.0, Ni=1.0)]
+    materials += [dict(Kd=(0, 0, 0), Ks=(0, 0, 0), Tr=(1, 1, 1), Ns=1.0, Ni=1.0) for _ in range(n_lights)]
+    lights = [(2 + l, (20.0 + 5 * l, 18.0, 12.0 - 2 * l)) for l in range(n_lights)]
+    cam = dict(eye=(0.0, 0.3, -4.5), lookat=(0.0, 0.0, 0.0), up=(0.0, 1.0, 0.0), fovy=45.0)
+    return dict(v9=v, vn9=vn, mtl=mtl, materials=materials, lights=lights, camera=cam, width=width, height=height)

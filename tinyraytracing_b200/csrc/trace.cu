@@ -70,7 +70,7 @@ struct BatchRays
     }
 };
 
-// 9 CTAs per SM (56 registers): the walker is latency-bound, see k_shadow in wavefront.cu
+// 9 CTAs per SM (56 registers): the walker is latency-bound, see k_walk in wavefront.cu
 #ifndef TRT_WALK_CTAS
 #define TRT_WALK_CTAS 9
 #endif

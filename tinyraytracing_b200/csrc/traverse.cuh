@@ -461,7 +461,7 @@ __device__ __forceinline__ void traceWide(const SceneView &sv, float3 S, float3 
 // pop loops alone — a local-memory load, a compare, a branch, at 2-4 lanes while the rest of the warp waits — hold
 // 20 % of all samples.  Two remedies were built and measured in round 2, and both lost: mirroring the
 // top stack entry in registers so that a pop only STARTS the load of the entry below (staircase 6.38 -> 6.18 Grays/s,
-// k_shadow 58.2 -> 61.2 ms: two more live registers at the 56-register cap), and handing a nearest child that is a leaf
+// shadow walk 58.2 -> 61.2 ms: two more live registers at the 56-register cap), and handing a nearest child that is a leaf
 // straight to the postponed-leaf slot instead of pushing and popping it back (6.38 -> 6.22: the six selects that shift
 // the sorted children run for every lane, the saved store + load only for a fifth of the visits).
 struct WalkState

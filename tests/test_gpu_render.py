@@ -21,9 +21,12 @@ def _compare(img, ref):
     return rmse / max(mean, 1e-12), close
 
 
+@pytest.mark.parametrize("tail", ("0", "default"))  # per-depth kernels to the end / k_finish (these frames: from depth 0)
 @pytest.mark.parametrize("name", SCENES)
-def test_render_matches_oracle(name, oracle_scenes, device_scenes):
+def test_render_matches_oracle(name, tail, oracle_scenes, device_scenes, monkeypatch):
     spp = 8
+    if tail != "default":
+        monkeypatch.setenv("TRT_TAIL_PATHS", tail)
     img = device_scenes[name].render(spp, seed=42)
     ref, counts = oracle_scenes[name].render(spp, seed=42)
     rel, close = _compare(img, ref)
@@ -59,6 +62,25 @@ def test_render_is_batch_and_shard_independent(device_scenes):
     assert np.allclose(img, a, rtol=1e-12, atol=0)
     # a different seed gives a different image (the streams really are keyed by the seed)
     assert not np.array_equal(dev.render(8, seed=6), a)
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_tail_kernel_switch_point_does_not_change_the_frame(name, device_scenes, monkeypatch):
+    """Below TRT_TAIL_PATHS live paths the rest of a batch runs in one launch (k_finish: one thread per path, light samples
+    walked on the spot) instead of two launches per depth.  Same per-path operations in the same order: the frame and the
+    ray counts must be identical wherever the switch happens — never, mid-way, or before the first vertex."""
+    dev = device_scenes[name]
+    got = []
+    for tail in ("0", "3000", str(1 << 30)):
+        monkeypatch.setenv("TRT_TAIL_PATHS", tail)
+        dev.reset_stats()
+        img = dev.render(5, seed=23, batch_paths=dev.width * dev.height * 2)  # three batches, the last one ragged
+        st = dev.stats()
+        got.append((img, int(st["rays_closest"]), int(st["rays_shadow"]), int(st["kernel_launches"])))
+    for img, closest, shadow, _ in got[1:]:
+        assert np.array_equal(img, got[0][0])
+        assert (closest, shadow) == got[0][1:3]
+    assert got[2][3] < got[1][3] < got[0][3]  # and the launches really were replaced
 
 
 def test_reftopo_render_identical(device_scenes):

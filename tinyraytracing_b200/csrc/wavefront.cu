@@ -41,6 +41,9 @@ namespace trt
 namespace
 {
 constexpr int kBlock = 128;
+#ifndef TRT_TAIL_PATHS_DEFAULT
+#define TRT_TAIL_PATHS_DEFAULT 65536
+#endif
 // k_shade is a long dependent chain per warp (ncu, profiles/r02_shade_staircase.txt: issue-active 44 %, 0.75 eligible warps
 // per cycle): its throughput is resident warps / that latency, so registers are traded for warps.  64-thread CTAs with a
 // minimum of 14 resident per SM cap it at 72 registers (88 bytes of spills) = 7 warps per scheduler.  k_shade's own
@@ -446,257 +449,343 @@ __device__ __forceinline__ void settleVertex(const WfBuffers &wf, int n_lights, 
 // -> 16.2 veach-mis): the kernel's time is load and dependency latency — ncu: 27 % of stall samples on loads, among them
 // the round trip of the shadow-queue atomic of every light iteration, 26 % on fixed-latency dependencies, 14 % on
 // instruction fetch — not the lanes its instructions serve.  DESIGN.md §10.)
+// One path vertex: settles the previous vertex, then shade() / nextRay() / RR() of pathTracing.cpp for the hit the walk
+// left in hit_id / hit_t[slot].  Returns whether the path goes on (its next ray is then in ray_o / ray_d[slot]).
+// TAIL = false: light-sample rays go to the per-light queues for the next k_walk; TAIL = true (k_finish): they are walked
+// here, one after the other, and their outcome is written straight into sh_contrib.
+template <bool TAIL>
+__device__ __forceinline__ bool shadeVertex(const SceneView &sv, const WfBuffers &wf, int slot, int depth, int max_depth, int sample0,
+                                            uint64_t seed, int npix, int pixel0, unsigned int &tail_shadow)
+{
+    bool survives = false;
+    uint32_t mask = 0;
+    float4 weight = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int tri = wf.hit_id[slot];
+    const float4 rd4 = wf.ray_d[slot];
+    const int via = __float_as_int(rd4.w);
+    if (depth > 0)
+    {
+        // the previous vertex: its light samples (their shadow rays were walked together with this path's ray),
+        // then throughput *= weight of the bounce that led here (:84-98)
+        float4 T = wf.thr[slot];
+        const uint32_t pm = wf.nee_mask[slot];
+        if (pm)
+        {
+            float4 L = wf.L[slot];
+            settleVertex(wf, sv.n_lights, slot, pm, T, L);
+            wf.L[slot] = L;
+        }
+        const float4 w = wf.weight[slot];
+        T.x *= w.x, T.y *= w.y, T.z *= w.z;
+        wf.thr[slot] = T;
+    }
+    if (tri >= 0)
+    {
+        const TriShade ts = sv.tri_shade[tri];
+        // material fields are fetched where they are used (L1-resident table) instead of holding the whole record
+        // in registers across the light loop: k_shade's occupancy is register-bound
+        const DeviceMaterial *mp = sv.materials + ts.mtl;
+        if (mp->is_emissive)
+        {
+            // :9-12 returns the radiance; DIFFUSE / SPECULAR arrivals drop it (:87-94), camera and
+            // TRANSMISSION arrivals keep it (main.cpp:101, :95-96)
+            if (via == CAMERA || via == TRANSMISSION)
+            {
+                const float4 T = wf.thr[slot];
+                float4 L = wf.L[slot];
+                const float3 rad = mp->radiance;
+                L.x += T.x * rad.x, L.y += T.y * rad.y, L.z += T.z * rad.z;
+                wf.L[slot] = L;
+            }
+        }
+        else
+        {
+            Rng rng{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(pixel0 + slot % npix), (uint32_t)(sample0 + slot / npix),
+                    (uint32_t)depth};
+            const float3 S = xyz(wf.ray_o[slot]), d = xyz(rd4);
+            const float3 wi = -d;
+            const float3 P = S + d * wf.hit_t[slot]; // bvh.cpp:191
+            float bx, by, bz;
+            baryLeastSquares(sv.tri_v + (size_t)tri * 9, P, bx, by, bz);
+            const float3 pn = shadingNormal(ts.vn, bx, by, bz); // bvh.cpp:223-224
+            float3 Kd = mp->Kd;
+            const int m_texture = mp->texture;
+            const float3 m_Ks = mp->Ks;
+            const float m_Ns = mp->Ns;
+            if (m_texture >= 0) // :17-26
+            {
+                const double col = (ts.vt[0] * bx + ts.vt[2] * by) + ts.vt[4] * bz;
+                const double row = (ts.vt[1] * bx + ts.vt[3] * by) + ts.vt[5] * bz;
+                const double irow = row - floor(row), icol = col - floor(col);
+                const DeviceTexture tx = sv.textures[m_texture];
+                // frac() of a tiny negative coordinate is exactly 1.0: the reference then reads past the image
+                // (:24, undefined); the oracle and this kernel clamp to the last texel
+                const int r = min((int)(irow * tx.rows), tx.rows - 1), c = min((int)(icol * tx.cols), tx.cols - 1);
+                const uint8_t *px = tx.bgr + ((size_t)r * tx.cols + c) * 3;
+                Kd = f3((float)((double)px[2] / 255), (float)((double)px[1] / 255), (float)((double)px[0] / 255));
+            }
+
+            // the same for every light: the diffuse BRDF term Kd / PI (:67) and |pn| (:63)
+            const float3 Kd_pi = divByPositive(Kd, kPI);
+            const float pn_len = length3(pn);
+
+            // ---- direct illumination :33-75
+            for (int li = 0; li < sv.n_lights; ++li)
+            {
+                const DeviceLight lt = sv.lights[li];
+                double u0[2];
+                rng.block(4 + 2 * li, u0);
+                const double rnd = u0[0] * sv.first_light_area; // quirk A.5-1 (:38)
+                // first light triangle whose cumulative area exceeds rnd: the reference walks the list
+                // linearly (:40-42).  rnd is drawn from [0, area of the FIRST light), so the answer is usually the
+                // first triangle or none at all; otherwise gallop, then bisect (cumulative areas are non-decreasing)
+                const double *cum = sv.light_cum_area + lt.first_tri;
+                const int nt = lt.n_tris;
+                if (nt == 0)
+                    continue;
+                int lo = 0;
+                if (!(rnd < __ldg(cum)))
+                {
+                    if (!(rnd < __ldg(cum + nt - 1)))
+                        continue; // no triangle selected: this light is not sampled at this vertex
+                    int a = 0, b = 1; // !(rnd < cum[a]); looking for the first b with rnd < cum[b]
+                    while (b < nt - 1 && !(rnd < __ldg(cum + b)))
+                        a = b, b = min(2 * b + 1, nt - 1);
+                    while (b - a > 1)
+                    {
+                        const int mid = (a + b) >> 1;
+                        if (rnd < __ldg(cum + mid))
+                            b = mid;
+                        else
+                            a = mid;
+                    }
+                    lo = b;
+                }
+                double u1[2];
+                rng.block(5 + 2 * li, u1);
+                const double rnd1 = u0[1], rnd2 = u1[0], rnd3 = u1[1];
+                const double rs = (rnd1 + rnd2) + rnd3;
+                const float p1 = (float)(rnd1 / rs), p2 = (float)(rnd2 / rs), p3 = (float)(rnd3 / rs);
+                const float *lv = sv.light_v + (size_t)(lt.first_tri + lo) * 9;
+                const float *ln = sv.light_vn + (size_t)(lt.first_tri + lo) * 9;
+                const float3 light_p = (f3(lv[0], lv[1], lv[2]) * p1 + f3(lv[3], lv[4], lv[5]) * p2) + f3(lv[6], lv[7], lv[8]) * p3;
+                const float3 light_n =
+                    normalize3((f3(ln[0], ln[1], ln[2]) * p1 + f3(ln[3], ln[4], ln[5]) * p2) + f3(ln[6], ln[7], ln[8]) * p3);
+                const float3 wo = normalize3(light_p - P);
+                const float wo_pn = dot3(wo, pn);
+                if (!(wo_pn > 0.f)) // :60 — the sample cannot contribute: the shadow ray is not traced
+                    continue;
+                const float3 radiance = sv.materials[lt.material].radiance;
+                const float pdf_light = lt.pdf; // (float)(double(1) / area) of :62, computed once per light on the host
+                const float cos_theta_p = fabsf(dot3(wo, light_n));
+                const float cos_theta = fabsf(wo_pn / pn_len);
+                const float3 diff = light_p - P;
+                const float len2 = dot3(diff, diff);
+                const float3 intensity = (((radiance * cos_theta_p) * cos_theta) / len2) / pdf_light;
+                const float3 h = normalize3((wi + wo) * 0.5f);
+                const double cos_alpha = fmax((double)dot3(pn, h), 0.0);
+                // Ks == 0 (every diffuse material): Ks * (Ns+2) * pow(...) is +0 for any finite power, and the
+                // power is finite for cos_alpha in [0,1] and Ns >= 0 — the double-precision pow is skipped
+                const bool no_spec = (m_Ks.x == 0.f) && (m_Ks.y == 0.f) && (m_Ks.z == 0.f) && (m_Ns >= 0.f);
+                // the specular term of a diffuse material is (+0 * (Ns + 2)) * 0 / 2pi = +0 in every channel
+                float3 spec_term = f3(0.f, 0.f, 0.f);
+                if (!no_spec)
+                {
+                    // cos^Ns below 2^-110 (a narrow lobe seen from outside it: most evaluations at Ns = 250..1000) is
+                    // taken as 0 without running the double-precision pow — a 300-instruction subroutine that ncu
+                    // shows at 4 lanes; what is dropped is below 1e-30 of the diffuse term it would be added to.
+                    // (cos_alpha = 0: log2 = -inf; Ns = 0: the product is NaN or 0 and the pow runs.)
+                    float pw = 0.f;
+                    if (!(m_Ns * __log2f((float)cos_alpha) < -110.f))
+                        pw = (float)pow(cos_alpha, (double)m_Ns);
+                    spec_term = divByPositive((m_Ks * (m_Ns + 2.0f)) * pw, 2.0f * kPI);
+                }
+                const float3 brdf = Kd_pi + spec_term;
+                const float3 contrib = intensity * brdf;
+                const int cidx = slot * sv.n_lights + li;
+                if (TAIL)
+                {
+                    // the light sample's ray walked on the spot (pathTracing.cpp:51-58: the CLOSEST hit decides; the
+                    // bounded search + retry of the queued form returns the same hit, see WalkRays)
+                    Hit sh;
+                    traceClosest(sv, P, wo, sh);
+                    ++tail_shadow;
+                    const bool visible = sh.id >= 0 && sv.tri_shade[sh.id].mtl == lt.material;
+                    wf.sh_contrib[cidx] = visible ? xyzw(contrib, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                else
+                {
+                    wf.sh_contrib[cidx] = xyzw(contrib, 0.f);
+                    // one queue segment per light, appended by the lanes that are converged here with a single
+                    // atomic: neighbouring entries are neighbouring pixels aiming at the same light
+                    cg::coalesced_group g = cg::coalesced_threads();
+                    int at = 0;
+                    if (g.thread_rank() == 0)
+                        at = atomicAdd(&wf.counters[kShadowCount + li], (int)g.size());
+                    at = g.shfl(at, 0);
+                    const size_t e = (size_t)li * wf.capacity + at + g.thread_rank();
+                    wf.sh_o[e] = xyzw(P, __int_as_float(cidx));
+                    // the light point lies at |diff| along wo (a unit vector up to rounding): search up to 1.001 x that
+                    wf.sh_d[e] = xyzw(wo, sqrtf(len2) * 1.001f);
+                }
+                mask |= 1u << li;
+            }
+
+            // ---- indirect :78-99
+            const bool may_bounce = (max_depth == 0) || (depth + 1 < max_depth);
+            double ur[2];
+            rng.block(1, ur);
+            if (may_bounce && ur[0] < (double)kPRR) // RR(): :104-109
+            {
+                // nextRay(): :147-209
+                const float3 ray_direction = d; // -wi
+                int type = INVALID;
+                float3 ndir = f3(0.f, 0.f, 0.f);
+                bool decided = false;
+                const float m_Ni = mp->Ni;
+                if (m_Ni > 1.f)
+                {
+                    double n1, n2;
+                    const double cos_in = (double)dot3(ray_direction, pn);
+                    float3 normal;
+                    if (cos_in > 0)
+                        normal = -pn, n1 = (double)m_Ni, n2 = 1.0;
+                    else
+                        normal = pn, n1 = 1.0, n2 = (double)m_Ni;
+                    const double q = (n1 - n2) / (n1 + n2);
+                    const double rf0 = q * q;
+                    const double a = (double)1.0f - fabs(cos_in);
+                    const double fresnel = rf0 + ((double)1.0f - rf0) * (((a * a) * (a * a)) * a);
+                    if (fresnel < ur[1])
+                    {
+                        const float eta = (float)(n1 / n2);
+                        const float dv = dot3(normal, ray_direction);
+                        const float k = 1.0f - eta * eta * (1.0f - dv * dv);
+                        if (k >= 0.0f)
+                            ndir = eta * ray_direction - (eta * dv + sqrtf(k)) * normal;
+                        if (ndir.x != 0.f || ndir.y != 0.f || ndir.z != 0.f)
+                            type = TRANSMISSION;
+                        else
+                            ndir = reflect3(ray_direction, normal), type = SPECULAR;
+                        decided = true;
+                    }
+                }
+                if (!decided)
+                {
+                    const double kd = mp->kd, ks = mp->ks; // |Kd| / (|Kd| + |Ks|), |Ks| / (...), :191-192 (host, once)
+                    double ul[2], ut[2];
+                    rng.block(2, ul);
+                    const double p = ul[0];
+                    if (p < kd)
+                    {
+                        rng.block(3, ut);
+                        ndir = sampleLobe(pn, DIFFUSE, (double)m_Ns, ul[1], ut[0]);
+                        type = DIFFUSE;
+                    }
+                    else if (m_Ns > 1.f && p < kd + ks)
+                    {
+                        rng.block(3, ut);
+                        ndir = sampleLobe(reflect3(ray_direction, pn), SPECULAR, (double)m_Ns, ul[1], ut[0]);
+                        type = SPECULAR;
+                    }
+                }
+                if (type != INVALID) // the reference traces the INVALID ray too and discards it (:81-82)
+                {
+                    const float3 w = (type == TRANSMISSION) ? mp->Tr : Kd; // SPECULAR also weights by Kd (:92-93)
+                    weight = xyzw(divByPositive(w, kPRR), 0.f);
+                    wf.ray_o[slot] = xyzw(P, 0.f);
+                    wf.ray_d[slot] = xyzw(ndir, __int_as_float(type));
+                    survives = true;
+                }
+            }
+        }
+    }
+    wf.nee_mask[slot] = mask;
+    wf.weight[slot] = weight;
+    return survives;
+}
+
+// K3: one thread per entry of the path queue.
 __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) k_shade(SceneView sv, WfBuffers wf, int qsel, int depth, int max_depth,
                                                   int sample0, uint64_t seed, int npix, int pixel0)
 {
-  pdlEntry();
-  const int count = wf.counters[qsel];
-  // warp-uniform grid-stride loop: the queue appends below are warp-collective
-  for (int base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x)
-  {
-    const int i = base + threadIdx.x;
-    const bool active = i < count;
-    bool survives = false;
-    int slot = 0;
-    uint32_t mask = 0;
-    float4 weight = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (active)
+    pdlEntry();
+    const int count = wf.counters[qsel];
+    unsigned int unused = 0;
+    // warp-uniform grid-stride loop: the queue append below is warp-collective
+    for (int base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x)
     {
-        slot = wf.queue[qsel][i];
-        const int tri = wf.hit_id[slot];
-        const float4 rd4 = wf.ray_d[slot];
-        const int via = __float_as_int(rd4.w);
-        if (depth > 0)
+        const int i = base + threadIdx.x;
+        bool survives = false;
+        int slot = 0;
+        if (i < count)
         {
-            // the previous vertex: its light samples (their shadow rays were walked together with this path's ray),
-            // then throughput *= weight of the bounce that led here (:84-98)
-            float4 T = wf.thr[slot];
-            const uint32_t pm = wf.nee_mask[slot];
-            if (pm)
-            {
-                float4 L = wf.L[slot];
-                settleVertex(wf, sv.n_lights, slot, pm, T, L);
-                wf.L[slot] = L;
-            }
-            const float4 w = wf.weight[slot];
-            T.x *= w.x, T.y *= w.y, T.z *= w.z;
-            wf.thr[slot] = T;
+            slot = wf.queue[qsel][i];
+            survives = shadeVertex<false>(sv, wf, slot, depth, max_depth, sample0, seed, npix, pixel0, unused);
         }
-        if (tri >= 0)
-        {
-            const TriShade ts = sv.tri_shade[tri];
-            // material fields are fetched where they are used (L1-resident table) instead of holding the whole record
-            // in registers across the light loop: k_shade's occupancy is register-bound
-            const DeviceMaterial *mp = sv.materials + ts.mtl;
-            if (mp->is_emissive)
-            {
-                // :9-12 returns the radiance; DIFFUSE / SPECULAR arrivals drop it (:87-94), camera and
-                // TRANSMISSION arrivals keep it (main.cpp:101, :95-96)
-                if (via == CAMERA || via == TRANSMISSION)
-                {
-                    const float4 T = wf.thr[slot];
-                    float4 L = wf.L[slot];
-                    const float3 rad = mp->radiance;
-                    L.x += T.x * rad.x, L.y += T.y * rad.y, L.z += T.z * rad.z;
-                    wf.L[slot] = L;
-                }
-            }
-            else
-            {
-                Rng rng{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(pixel0 + slot % npix), (uint32_t)(sample0 + slot / npix),
-                        (uint32_t)depth};
-                const float3 S = xyz(wf.ray_o[slot]), d = xyz(rd4);
-                const float3 wi = -d;
-                const float3 P = S + d * wf.hit_t[slot]; // bvh.cpp:191
-                float bx, by, bz;
-                baryLeastSquares(sv.tri_v + (size_t)tri * 9, P, bx, by, bz);
-                const float3 pn = shadingNormal(ts.vn, bx, by, bz); // bvh.cpp:223-224
-                float3 Kd = mp->Kd;
-                const int m_texture = mp->texture;
-                const float3 m_Ks = mp->Ks;
-                const float m_Ns = mp->Ns;
-                if (m_texture >= 0) // :17-26
-                {
-                    const double col = (ts.vt[0] * bx + ts.vt[2] * by) + ts.vt[4] * bz;
-                    const double row = (ts.vt[1] * bx + ts.vt[3] * by) + ts.vt[5] * bz;
-                    const double irow = row - floor(row), icol = col - floor(col);
-                    const DeviceTexture tx = sv.textures[m_texture];
-                    // frac() of a tiny negative coordinate is exactly 1.0: the reference then reads past the image
-                    // (:24, undefined); the oracle and this kernel clamp to the last texel
-                    const int r = min((int)(irow * tx.rows), tx.rows - 1), c = min((int)(icol * tx.cols), tx.cols - 1);
-                    const uint8_t *px = tx.bgr + ((size_t)r * tx.cols + c) * 3;
-                    Kd = f3((float)((double)px[2] / 255), (float)((double)px[1] / 255), (float)((double)px[0] / 255));
-                }
-
-                // the same for every light: the diffuse BRDF term Kd / PI (:67) and |pn| (:63)
-                const float3 Kd_pi = divByPositive(Kd, kPI);
-                const float pn_len = length3(pn);
-
-                // ---- direct illumination :33-75
-                for (int li = 0; li < sv.n_lights; ++li)
-                {
-                    const DeviceLight lt = sv.lights[li];
-                    double u0[2];
-                    rng.block(4 + 2 * li, u0);
-                    const double rnd = u0[0] * sv.first_light_area; // quirk A.5-1 (:38)
-                    // first light triangle whose cumulative area exceeds rnd: the reference walks the list
-                    // linearly (:40-42).  rnd is drawn from [0, area of the FIRST light), so the answer is usually the
-                    // first triangle or none at all; otherwise gallop, then bisect (cumulative areas are non-decreasing)
-                    const double *cum = sv.light_cum_area + lt.first_tri;
-                    const int nt = lt.n_tris;
-                    if (nt == 0)
-                        continue;
-                    int lo = 0;
-                    if (!(rnd < __ldg(cum)))
-                    {
-                        if (!(rnd < __ldg(cum + nt - 1)))
-                            continue; // no triangle selected: this light is not sampled at this vertex
-                        int a = 0, b = 1; // !(rnd < cum[a]); looking for the first b with rnd < cum[b]
-                        while (b < nt - 1 && !(rnd < __ldg(cum + b)))
-                            a = b, b = min(2 * b + 1, nt - 1);
-                        while (b - a > 1)
-                        {
-                            const int mid = (a + b) >> 1;
-                            if (rnd < __ldg(cum + mid))
-                                b = mid;
-                            else
-                                a = mid;
-                        }
-                        lo = b;
-                    }
-                    double u1[2];
-                    rng.block(5 + 2 * li, u1);
-                    const double rnd1 = u0[1], rnd2 = u1[0], rnd3 = u1[1];
-                    const double rs = (rnd1 + rnd2) + rnd3;
-                    const float p1 = (float)(rnd1 / rs), p2 = (float)(rnd2 / rs), p3 = (float)(rnd3 / rs);
-                    const float *lv = sv.light_v + (size_t)(lt.first_tri + lo) * 9;
-                    const float *ln = sv.light_vn + (size_t)(lt.first_tri + lo) * 9;
-                    const float3 light_p = (f3(lv[0], lv[1], lv[2]) * p1 + f3(lv[3], lv[4], lv[5]) * p2) + f3(lv[6], lv[7], lv[8]) * p3;
-                    const float3 light_n =
-                        normalize3((f3(ln[0], ln[1], ln[2]) * p1 + f3(ln[3], ln[4], ln[5]) * p2) + f3(ln[6], ln[7], ln[8]) * p3);
-                    const float3 wo = normalize3(light_p - P);
-                    const float wo_pn = dot3(wo, pn);
-                    if (!(wo_pn > 0.f)) // :60 — the sample cannot contribute: the shadow ray is not traced
-                        continue;
-                    const float3 radiance = sv.materials[lt.material].radiance;
-                    const float pdf_light = lt.pdf; // (float)(double(1) / area) of :62, computed once per light on the host
-                    const float cos_theta_p = fabsf(dot3(wo, light_n));
-                    const float cos_theta = fabsf(wo_pn / pn_len);
-                    const float3 diff = light_p - P;
-                    const float len2 = dot3(diff, diff);
-                    const float3 intensity = (((radiance * cos_theta_p) * cos_theta) / len2) / pdf_light;
-                    const float3 h = normalize3((wi + wo) * 0.5f);
-                    const double cos_alpha = fmax((double)dot3(pn, h), 0.0);
-                    // Ks == 0 (every diffuse material): Ks * (Ns+2) * pow(...) is +0 for any finite power, and the
-                    // power is finite for cos_alpha in [0,1] and Ns >= 0 — the double-precision pow is skipped
-                    const bool no_spec = (m_Ks.x == 0.f) && (m_Ks.y == 0.f) && (m_Ks.z == 0.f) && (m_Ns >= 0.f);
-                    // the specular term of a diffuse material is (+0 * (Ns + 2)) * 0 / 2pi = +0 in every channel
-                    float3 spec_term = f3(0.f, 0.f, 0.f);
-                    if (!no_spec)
-                    {
-                        // cos^Ns below 2^-110 (a narrow lobe seen from outside it: most evaluations at Ns = 250..1000) is
-                        // taken as 0 without running the double-precision pow — a 300-instruction subroutine that ncu
-                        // shows at 4 lanes; what is dropped is below 1e-30 of the diffuse term it would be added to.
-                        // (cos_alpha = 0: log2 = -inf; Ns = 0: the product is NaN or 0 and the pow runs.)
-                        float pw = 0.f;
-                        if (!(m_Ns * __log2f((float)cos_alpha) < -110.f))
-                            pw = (float)pow(cos_alpha, (double)m_Ns);
-                        spec_term = divByPositive((m_Ks * (m_Ns + 2.0f)) * pw, 2.0f * kPI);
-                    }
-                    const float3 brdf = Kd_pi + spec_term;
-                    const float3 contrib = intensity * brdf;
-                    const int cidx = slot * sv.n_lights + li;
-                    wf.sh_contrib[cidx] = xyzw(contrib, 0.f);
-                    {
-                        // one queue segment per light, appended by the lanes that are converged here with a single
-                        // atomic: neighbouring entries are neighbouring pixels aiming at the same light
-                        cg::coalesced_group g = cg::coalesced_threads();
-                        int at = 0;
-                        if (g.thread_rank() == 0)
-                            at = atomicAdd(&wf.counters[kShadowCount + li], (int)g.size());
-                        at = g.shfl(at, 0);
-                        const size_t e = (size_t)li * wf.capacity + at + g.thread_rank();
-                        wf.sh_o[e] = xyzw(P, __int_as_float(cidx));
-                        // the light point lies at |diff| along wo (a unit vector up to rounding): search up to 1.001 x that
-                        wf.sh_d[e] = xyzw(wo, sqrtf(len2) * 1.001f);
-                    }
-                    mask |= 1u << li;
-                }
-
-                // ---- indirect :78-99
-                const bool may_bounce = (max_depth == 0) || (depth + 1 < max_depth);
-                double ur[2];
-                rng.block(1, ur);
-                if (may_bounce && ur[0] < (double)kPRR) // RR(): :104-109
-                {
-                    // nextRay(): :147-209
-                    const float3 ray_direction = d; // -wi
-                    int type = INVALID;
-                    float3 ndir = f3(0.f, 0.f, 0.f);
-                    bool decided = false;
-                    const float m_Ni = mp->Ni;
-                    if (m_Ni > 1.f)
-                    {
-                        double n1, n2;
-                        const double cos_in = (double)dot3(ray_direction, pn);
-                        float3 normal;
-                        if (cos_in > 0)
-                            normal = -pn, n1 = (double)m_Ni, n2 = 1.0;
-                        else
-                            normal = pn, n1 = 1.0, n2 = (double)m_Ni;
-                        const double q = (n1 - n2) / (n1 + n2);
-                        const double rf0 = q * q;
-                        const double a = (double)1.0f - fabs(cos_in);
-                        const double fresnel = rf0 + ((double)1.0f - rf0) * (((a * a) * (a * a)) * a);
-                        if (fresnel < ur[1])
-                        {
-                            const float eta = (float)(n1 / n2);
-                            const float dv = dot3(normal, ray_direction);
-                            const float k = 1.0f - eta * eta * (1.0f - dv * dv);
-                            if (k >= 0.0f)
-                                ndir = eta * ray_direction - (eta * dv + sqrtf(k)) * normal;
-                            if (ndir.x != 0.f || ndir.y != 0.f || ndir.z != 0.f)
-                                type = TRANSMISSION;
-                            else
-                                ndir = reflect3(ray_direction, normal), type = SPECULAR;
-                            decided = true;
-                        }
-                    }
-                    if (!decided)
-                    {
-                        const double kd = mp->kd, ks = mp->ks; // |Kd| / (|Kd| + |Ks|), |Ks| / (...), :191-192 (host, once)
-                        double ul[2], ut[2];
-                        rng.block(2, ul);
-                        const double p = ul[0];
-                        if (p < kd)
-                        {
-                            rng.block(3, ut);
-                            ndir = sampleLobe(pn, DIFFUSE, (double)m_Ns, ul[1], ut[0]);
-                            type = DIFFUSE;
-                        }
-                        else if (m_Ns > 1.f && p < kd + ks)
-                        {
-                            rng.block(3, ut);
-                            ndir = sampleLobe(reflect3(ray_direction, pn), SPECULAR, (double)m_Ns, ul[1], ut[0]);
-                            type = SPECULAR;
-                        }
-                    }
-                    if (type != INVALID) // the reference traces the INVALID ray too and discards it (:81-82)
-                    {
-                        const float3 w = (type == TRANSMISSION) ? mp->Tr : Kd; // SPECULAR also weights by Kd (:92-93)
-                        weight = xyzw(divByPositive(w, kPRR), 0.f);
-                        wf.ray_o[slot] = xyzw(P, 0.f);
-                        wf.ray_d[slot] = xyzw(ndir, __int_as_float(type));
-                        survives = true;
-                    }
-                }
-            }
-        }
-        wf.nee_mask[slot] = mask;
-        wf.weight[slot] = weight;
+        appendQueue(&wf.counters[qsel ^ 1], wf.queue[qsel ^ 1], survives, slot);
     }
-    appendQueue(&wf.counters[qsel ^ 1], wf.queue[qsel ^ 1], survives, slot);
-  }
+}
+
+// The tail of a batch in ONE launch: once few paths are left, every depth costs two launches of almost no work — a
+// 512x512 16-spp job is 42 depths, 30 of them with fewer paths than the GPU has threads — so from there on each remaining
+// path is run to its end by one thread: shadeVertex<true> (light samples walked on the spot), then the walk of the next
+// ray, until the path dies.  The same device functions on the same per-path state in the same order as the per-depth
+// kernels: the frame is bit-identical whatever the switch point (TRT_TAIL_PATHS, tests/test_gpu_render.py).
+// Lanes of a warp stay in step (all shade, then all walk); what is lost is lanes of paths that have ended.
+// The last CTA publishes the snapshot that tells the host the batch is over, with the rays traced here in two spare
+// counters (trt_stats).
+constexpr int kTailClosest = 4, kTailShadow = 5;
+#ifndef TRT_FINISH_MINBLOCKS
+#define TRT_FINISH_MINBLOCKS 4 // 158 registers, no spills (8: 113 registers, within 0.5 %)
+#endif
+__global__ void __launch_bounds__(kShadeBlock, TRT_FINISH_MINBLOCKS) k_finish(SceneView sv, WfBuffers wf, int qsel, int depth0, int max_depth, int sample0,
+                                                        uint64_t seed, int npix, int pixel0, int32_t *snap, int32_t seq)
+{
+    pdlEntry();
+    const int count = wf.counters[qsel];
+    unsigned int n_closest = 0, n_shadow = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    {
+        const int slot = wf.queue[qsel][i];
+        for (int depth = depth0; shadeVertex<true>(sv, wf, slot, depth, max_depth, sample0, seed, npix, pixel0, n_shadow); ++depth)
+        {
+            Hit h;
+            traceClosest(sv, xyz(wf.ray_o[slot]), xyz(wf.ray_d[slot]), h);
+            wf.hit_id[slot] = h.id, wf.hit_t[slot] = h.t;
+            ++n_closest;
+        }
+    }
+    __syncwarp();
+    n_closest = __reduce_add_sync(0xffffffffu, n_closest), n_shadow = __reduce_add_sync(0xffffffffu, n_shadow);
+    if ((threadIdx.x & 31) == 0)
+    {
+        if (n_closest)
+            atomicAdd(&wf.counters[kTailClosest], (int)n_closest);
+        if (n_shadow)
+            atomicAdd(&wf.counters[kTailShadow], (int)n_shadow);
+    }
+    __syncthreads();
+    __shared__ bool s_last;
+    if (threadIdx.x == 0)
+    {
+        __threadfence();
+        s_last = atomicAdd(reinterpret_cast<unsigned int *>(wf.counters + kDone), 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && snap)
+    {
+        // the batch is over: both queues read as empty, no light samples pending
+        if (threadIdx.x < kNumCounters)
+        {
+            const bool kept = threadIdx.x == kTailClosest || threadIdx.x == kTailShadow;
+            snap[threadIdx.x] = kept ? __ldcg(wf.counters + threadIdx.x) : 0;
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            *reinterpret_cast<volatile int32_t *>(snap + kNumCounters) = seq;
+    }
 }
 
 // accum[pixel] += L of the batch's samples, ONE AT A TIME in sample order: the running double sum then goes through the
@@ -911,6 +1000,15 @@ static long long batchTarget(trt_scene *s, int batch_paths, long long &max_paths
 // in the counter snapshots that have arrived (runToEnd drives it; a host that has other work can interleave it).
 // Stream keys of slot: pixel = pixel0 + slot % npix, sample = sample0 + slot / npix.  first_walk = false: the hits of
 // depth 0 are already in hit_id / hit_t (trt_shade).  prof_ms (TRT_RENDER_PROFILE) += {closest-hit walk, shadow walk, shade}.
+// Switch point of k_finish: live paths at or below which the rest of a batch is run by one launch (0: never).
+// Measured on the 512x512 16-spp Cornell job: 4.38 ms without, 4.06 / 3.96 / 3.97 / 4.04 ms at 16 Ki / 64 Ki / 128 Ki /
+// 256 Ki paths (profiles/r02_ab_tail.txt); read at every batch so that tests can move it (TRT_TAIL_PATHS).
+static long long tailPaths()
+{
+    const char *e = getenv("TRT_TAIL_PATHS");
+    return e ? std::max(0ll, atoll(e)) : (long long)TRT_TAIL_PATHS_DEFAULT;
+}
+
 class DepthLoop
 {
   public:
@@ -928,6 +1026,7 @@ class DepthLoop
         mode = (flags & TRT_RENDER_REFTOPO) ? 1 : ((flags & TRT_RENDER_PLAIN) ? 2 : 0);
         profile = (flags & TRT_RENDER_PROFILE) != 0 && prof_ms;
         pdl = usePdl() && !profile; // (the profile's event records sit between the kernels)
+        tail_paths = profile ? 0 : tailPaths(); // (a profile lists every depth's kernels)
         nl = s->view.n_lights;
         seq0 = w->seq;
         q = 0, depth = 0, consumed = 0, dead = false, final_walk = false, prof_used = 0, live_bound = n_paths;
@@ -944,7 +1043,9 @@ class DepthLoop
             consume(consumed++);
             progress = 1;
         }
-        if (!dead)
+        if (final_walk)
+            ; // k_finish (or the last walk) is on its way: only its snapshot is still to come
+        else if (!dead)
         {
             if (depth - consumed <= kLag) // the host runs at most kLag depths ahead of what it has seen
             {
@@ -953,7 +1054,7 @@ class DepthLoop
                 progress = 1;
             }
         }
-        else if (!final_walk)
+        else
         {
             // one more walk: it serves whatever light samples the last k_shade emitted and publishes its counters
             walk(q, 1 | 2 | 4, 1, depth - 1);
@@ -1011,6 +1112,7 @@ class DepthLoop
     int q = 0, depth = 0, consumed = 0;
     bool dead = false, final_walk = false;
     long long live_bound = 0; // no queue from here on is longer
+    long long tail_paths = 0; // at or below this many live paths the rest of the batch is one k_finish launch
     size_t prof_used = 0;
 
     size_t slotOf(int it) const { return (size_t)(it % Wavefront::kRing) * Wavefront::kSlot; }
@@ -1029,8 +1131,8 @@ class DepthLoop
         uint64_t shadow = 0;
         for (int l = 0; l < nl; ++l)
             shadow += (uint64_t)c[kShadowCount + l];
-        s->stats.rays_shadow += shadow;
-        s->stats.rays_closest += (uint64_t)next_live; // traced by iteration it + 1
+        s->stats.rays_shadow += shadow + (uint64_t)c[kTailShadow]; // (the spare counters are zero except in k_finish's snapshot)
+        s->stats.rays_closest += (uint64_t)next_live + (uint64_t)c[kTailClosest]; // traced by iteration it + 1 / by k_finish
         if (!dead)
             live_bound = next_live;
         if (next_live == 0)
@@ -1089,6 +1191,19 @@ class DepthLoop
             walk(q, 1 | 2 | 4, live_bound + sh_bound, depth - 1);
         else if (walk_closest)
             walk(q, 1 | 4, live_bound, -1);
+        if (live_bound <= tail_paths)
+        {
+            // few paths left: this depth's vertices and everything after them in one launch
+            const long long grid = std::min((long long)s->sm_count * 32, std::max(1ll, (live_bound + kShadeBlock - 1) / kShadeBlock));
+            launchPdl(k_finish, (unsigned)grid, kShadeBlock, stream, pdl, s->view, w->buf, q, depth, max_depth, sample0, seed, npix, pixel0,
+                      w->d_ring + slotOf(depth), seq0 + 1 + depth);
+            s->stats.kernel_launches++;
+            ++depth;
+            w->seq = seq0 + depth;
+            final_walk = true;
+            TRT_CUDA(cudaGetLastError());
+            return TRT_OK;
+        }
         // k_shade: at most the resident CTAs (grid-stride loop inside): a second, partly filled wave of CTAs would cost a
         // whole extra pass of ~40 us warp iterations
         const long long full_shade = (long long)s->sm_count * std::max(1, w->blocks_shade);

@@ -696,7 +696,7 @@ def render_measurements(args, tmp, rank, world, local, barrier):
         frame = dev.pinned_image()  # the frame lands in page-locked host memory (valid until dev.close())
         # timed repetitions: the median is reported (a one-off stall of several ms shows up now and then in the first
         # render after another process's activity, and in the few-ms renders of config 1 at N > 1), the list is printed
-        reps = {"config1_cornell_shell": 9, "config3_veach_mis": 3}.get(key, 1)
+        reps = {"config1_cornell_shell": 9, "config3_veach_mis": 3 if world == 1 else 7}.get(key, 1)
         rec = {"scene": name, "width": w, "height": h, "spp": spp}
         if world == 1:
             dev.render(spp, seed=2, out=frame)  # warm-up at full size: allocates the wavefront buffers

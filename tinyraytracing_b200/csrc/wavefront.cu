@@ -9,6 +9,8 @@
 //   k_shade       (K3)  first settles the path's previous vertex — L[slot] += throughput * sum(visible light samples,
 //                       XML order); throughput *= weight — then shade(): emissive return, Kd/texture, per-light NEE
 //                       sample (emits shadow rays), RR, nextRay/Sample -> next ray, weight, next queue
+//   k_finish            the tail of a batch: once few paths are alive, ONE launch runs each of them to its end (the
+//                       same shade / walk device functions, one thread per path) instead of two launches per depth
 //   k_deposit           after the batch: settles the last vertex of every path the same way, then
 //                       accum[pixel] += sum over the batch's samples of L (double, fixed order)
 //   k_resolve     (K4)  accum / spp (main.cpp:101) and the gamma-2.2 8-bit pack of imshow (main.cpp:30-38)

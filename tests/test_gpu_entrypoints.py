@@ -10,10 +10,13 @@ from conftest import SCENES, make_rays
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("tail", ("default", "0"))  # k_finish from the first vertex (6000 records) / per-depth kernels only
 @pytest.mark.parametrize("name", SCENES)
-def test_shade_batch_matches_oracle(name, host_scenes, oracle_scenes, device_scenes):
+def test_shade_batch_matches_oracle(name, tail, host_scenes, oracle_scenes, device_scenes, monkeypatch):
     """shade(hit, wi) for a batch of traced rays: NEE + Russian roulette + the whole bounce chain from caller-supplied
     hits, against the oracle's recursive shade() on the same records with the same Philox streams (pixel key = index)."""
+    if tail != "default":
+        monkeypatch.setenv("TRT_TAIL_PATHS", tail)
     dev, orc = device_scenes[name], oracle_scenes[name]
     rays = make_rays(host_scenes[name], orc, 6000, seed=99)
     ids, t = dev.trace_closest(rays)

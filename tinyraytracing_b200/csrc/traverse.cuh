@@ -179,16 +179,23 @@ __device__ __forceinline__ void scanLeaf(const SceneView &sv, int first, int num
         TriGeom g;
         g.q0 = __ldg(gp), g.q1 = __ldg(gp + 1), g.q2 = __ldg(gp + 2);
         float t;
-        if (triangleHit(g, S, d, hit.t, t))
+        if (!trianglePlane(g.q0, g.q1, S, d, hit.t, t))
+            continue;
+        // the reference leaf of a candidate is fetched before the inside test, not after it: the gate below is two
+        // dependent loads (leaf index, then its box), and the first one's latency now hides behind the inside test
+        int32_t ref_leaf = 0;
+        if (FAST)
+            ref_leaf = __ldg(sv.fast_leaf + i);
+        if (triangleInside(g.q0, g.q1, g.q2, S, d, t))
         {
             if (FAST && pathGate)
             {
-                if (!refPathPasses(sv.ref_leaf_parent, sv.ref_nodes, __ldg(sv.fast_leaf + i), S, d))
+                if (!refPathPasses(sv.ref_leaf_parent, sv.ref_nodes, ref_leaf, S, d))
                     continue;
             }
             else if (FAST && sv.check_leaf_box)
             {
-                const float4 *bp = sv.ref_leaf_box + 2 * __ldg(sv.fast_leaf + i);
+                const float4 *bp = sv.ref_leaf_box + 2 * ref_leaf;
                 const float4 lo = __ldg(bp), hi = __ldg(bp + 1);
                 float t0;
                 if (!childPass(S, inv, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, t0))

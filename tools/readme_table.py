@@ -27,7 +27,7 @@ renders run inside the library (`trt_render_multi`: one process, N GPUs, scene r
 | config 5: 10 M triangles, 3840x2160, 8 spp | {s5['render_1gpu_nccl']['ms']:.1f} ms | — | — | {s5['render_8gpu_nccl']['ms']:.1f} ms | — |
 
 Round 1 → round 2 on one GPU: closest hit 15.6 → {n1['value']/1e3:.1f} Grays/s, config 1 6.46 → {r1[c1]['ms']:.2f} ms, config 3 436 → {r1[c3]['ms']:.0f} ms (staircase
-1280x720x16: 104 → 87 ms), 10 M-triangle mesh 3.05 → {n1['other_scenes']['stress_10m']['closest_hit_mrays']/1e3:.2f} Grays/s; config 3 on 8 GPUs 57.6 → {r8[c3]['ms']:.1f} ms (efficiency 0.947 →
+1280x720x16: 104 → 82.5 ms), 10 M-triangle mesh 3.05 → {n1['other_scenes']['stress_10m']['closest_hit_mrays']/1e3:.2f} Grays/s; config 3 on 8 GPUs 57.6 → {r8[c3]['ms']:.1f} ms (efficiency 0.947 →
 {r1[c3]['ms']/(8*r8[c3]['ms']):.3f}), config 4 on 8 GPUs 1.75 → {r8['config4_staircase']['ms']/1e3:.2f} s.
 
 '''

@@ -816,6 +816,8 @@ __global__ void __launch_bounds__(kShadeBlock, TRT_FINISH_MINBLOCKS) k_finish(Sc
         if (threadIdx.x == 0)
             *reinterpret_cast<volatile int32_t *>(snap + kNumCounters) = seq;
     }
+    if (s_last && threadIdx.x == 0) // leave the counters as the last walk of a batch leaves them
+        wf.counters[kDone] = 0, wf.counters[qsel] = 0, wf.counters[kTailClosest] = 0, wf.counters[kTailShadow] = 0;
 }
 
 // accum[pixel] += L of the batch's samples, ONE AT A TIME in sample order: the running double sum then goes through the

@@ -84,10 +84,14 @@ def test_tail_kernel_switch_point_does_not_change_the_frame(name, device_scenes,
 
 
 def test_reftopo_render_identical(device_scenes):
-    from tinyraytracing_b200.api import RENDER_REFTOPO
+    from tinyraytracing_b200.api import RENDER_PLAIN, RENDER_REFTOPO
 
+    # the two flags keep the per-depth kernels to the end of every path (no k_finish), each with its own walk: the
+    # reference topology / the fast layout thread per ray — independent checks of the default render
     dev = device_scenes["staircase"]
-    assert np.array_equal(dev.render(2, seed=1), dev.render(2, seed=1, flags=RENDER_REFTOPO))
+    ref = dev.render(2, seed=1)
+    assert np.array_equal(ref, dev.render(2, seed=1, flags=RENDER_REFTOPO))
+    assert np.array_equal(ref, dev.render(2, seed=1, flags=RENDER_PLAIN))
 
 
 def test_ray_counts(oracle_scenes, device_scenes):

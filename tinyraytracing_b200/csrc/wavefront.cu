@@ -1058,7 +1058,9 @@ class DepthLoop
         mode = (flags & TRT_RENDER_REFTOPO) ? 1 : ((flags & TRT_RENDER_PLAIN) ? 2 : 0);
         profile = (flags & TRT_RENDER_PROFILE) != 0 && prof_ms;
         pdl = usePdl() && !profile; // (the profile's event records sit between the kernels)
-        tail_paths = profile ? 0 : tailPaths(); // (a profile lists every depth's kernels)
+        // (a profile lists every depth's kernels; TRT_RENDER_REFTOPO / _PLAIN ask for one particular walk to the end of
+        // every path — k_finish walks the fast layout thread per ray — so that they stay independent checks of it)
+        tail_paths = (profile || mode != 0) ? 0 : tailPaths();
         nl = s->view.n_lights;
         seq0 = w->seq;
         q = 0, depth = 0, consumed = 0, dead = false, final_walk = false, prof_used = 0, live_bound = n_paths;

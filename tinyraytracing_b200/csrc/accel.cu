@@ -4,7 +4,9 @@
 #include <algorithm>
 #include <array>
 #include <atomic>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <future>
 #include <memory>
 #include <cstdlib>
@@ -580,6 +582,16 @@ std::string buildWide(const trt_scene_desc &desc, AccelBuild &out)
     out.ref_leaf_box.clear();
     out.light_box.clear();
     const int nn = desc.n_nodes, n = desc.n_tris;
+    // TRT_BUILD_TIMING: host-clock phases of this function on stderr (diagnostics)
+    const bool timing = getenv("TRT_BUILD_TIMING") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto phase = [&](const char *what) {
+        if (!timing)
+            return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "buildWide: %-28s %8.3f s\n", what, std::chrono::duration<double>(now - t_prev).count());
+        t_prev = now;
+    };
     const char *env = getenv("TRT_WIDE_SOURCE");
     const std::string mode = env ? env : "triangles";
     if (mode == "off")
@@ -713,12 +725,14 @@ std::string buildWide(const trt_scene_desc &desc, AccelBuild &out)
 
     const char *lenv = getenv("TRT_FAST_LEAF"); // triangles per leaf of the fast layout (1..8), default 2: measured best on every scene from 26 to 10 M triangles
     const int maxLeafTris = lenv ? std::max(1, std::min(8, atoi(lenv))) : 2;
+    phase("scan units (boxes, pads)");
     WideBuilder wb{prims, leafMode ? 1 : maxLeafTris, {}, {}};
     wb.order.resize(prims.size());
     for (size_t i = 0; i < prims.size(); ++i)
         wb.order[i] = (int32_t)i;
     wb.bn.resize(prims.size() * 2);
     wb.build(0, (int)prims.size());
+    phase("binned-SAH binary build");
     {
         // insertion-based optimisation (Reinserter above): up to two passes (one beyond 500 k triangles, where a pass
         // costs seconds), keeping whichever tree — the binned-SAH one included — collapses to the cheapest 4-wide tree
@@ -746,6 +760,7 @@ std::string buildWide(const trt_scene_desc &desc, AccelBuild &out)
         }
     }
     const std::vector<BNode> &bn = wb.bn;
+    phase("reinsertion passes");
 
     // triangles of a binary leaf, appended to the fast arrays in leaf order; returns the leaf link
     auto emitLeaf = [&](const BNode &c) -> int32_t {
@@ -855,6 +870,7 @@ std::string buildWide(const trt_scene_desc &desc, AccelBuild &out)
         w.link = make_int4(link[0], link[1], link[2], link[3]);
         w.pad = make_int4(0, 0, 0, 0);
     }
+    phase("collapse + emission");
     out.wide_root = 0;
     out.wide_depth = maxDepth;
     out.sah_wide = sah;

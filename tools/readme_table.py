@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Regenerates the measurement table of README.md from the bench lines under profiles/ (r02_bench_n{1,2,4,8}.json,
-r02_stress_config5_8gpu.json), so that the table is what was measured and nothing else.  usage: tools/readme_table.py"""
+r02_bench_n1_config4.json, r02_stress_config5_8gpu.json), so that the table is what was measured and nothing else.  usage: tools/readme_table.py"""
 import json
 import os
 
@@ -8,6 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P = lambda f: json.load(open(os.path.join(ROOT, "profiles", f)))
 n1, n2, n4, n8, s5 = P("r02_bench_n1.json"), P("r02_bench_n2.json"), P("r02_bench_n4.json"), P("r02_bench_n8.json"), P("r02_stress_config5_8gpu.json")
 r1, r2, r4, r8 = n1["render"], n2["render"], n4["render"], n8["render"]
+r1c4 = P("r02_bench_n1_config4.json")["render"]["config4_staircase"]  # bench.py --config4 --no-cpu --no-stress, 1 GPU
 c1, c3 = "config1_cornell_shell", "config3_veach_mis"
 new = f'''Measured on B200 (round 2, final build; raw lines: `profiles/r02_bench_n1.json`, `r02_bench_n2.json`,
 `r02_bench_n4.json`, `r02_bench_n8.json`; config 5: `r02_stress_config5_8gpu.json`, taken a few commits earlier; the table
@@ -23,7 +24,7 @@ renders run inside the library (`trt_render_multi`: one process, N GPUs, scene r
 | closest-hit, labelled stand-in for the missing cornell-box.obj (Cornell shell + 100 k-triangle sphere) | {n1['cornell_standin']['closest_hit_mrays']/1e3:.1f} Grays/s | — | — | — | — |
 | config 1: Cornell shell 512x512, 16 spp | {r1[c1]['spp_per_s']:.0f} spp/s ({r1[c1]['ms']:.2f} ms) | {r2[c1]['spp_per_s']:.0f} | {r4[c1]['spp_per_s']:.0f} | {r8[c1]['spp_per_s']:.0f} spp/s ({r8[c1]['ms']:.2f} ms) | {r1[c1]['cpu_reference']['spp_per_s_at_config']:.1f} spp/s (the unmodified program, {r1[c1]['cpu_reference']['sample']}) |
 | config 3: veach-mis 1280x720, 256 spp | {r1[c3]['spp_per_s']:.0f} spp/s ({r1[c3]['ms']:.0f} ms) | {r2[c3]['spp_per_s']:.0f} | {r4[c3]['spp_per_s']:.0f} | {r8[c3]['spp_per_s']:.0f} spp/s ({r8[c3]['ms']:.1f} ms) | {r1[c3]['cpu_reference']['spp_per_s_at_config']:.2f} spp/s (scaled from {r1[c3]['cpu_reference']['sample']}) |
-| config 4: staircase 1920x1080, 1024 spp (37 G rays) | — | — | — | {r8['config4_staircase']['spp_per_s']:.0f} spp/s ({r8['config4_staircase']['ms']/1e3:.2f} s) | — |
+| config 4: staircase 1920x1080, 1024 spp (37 G rays) | {r1c4['spp_per_s']:.1f} spp/s ({r1c4['ms']/1e3:.2f} s) | — | — | {r8['config4_staircase']['spp_per_s']:.0f} spp/s ({r8['config4_staircase']['ms']/1e3:.2f} s; efficiency {r1c4['ms']/(8*r8['config4_staircase']['ms']):.2f}, same 8-bit frame) | — |
 | config 5: 10 M triangles, 3840x2160, 8 spp | {s5['render_1gpu_nccl']['ms']:.1f} ms | — | — | {s5['render_8gpu_nccl']['ms']:.1f} ms | — |
 
 Round 1 → round 2 on one GPU: closest hit 15.6 → {n1['value']/1e3:.1f} Grays/s, config 1 6.46 → {r1[c1]['ms']:.2f} ms, config 3 436 → {r1[c3]['ms']:.0f} ms (staircase

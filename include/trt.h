@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TRT_VERSION 200
+#define TRT_VERSION 201
 
 typedef enum trt_status {
     TRT_OK = 0,
@@ -109,6 +109,16 @@ int trt_device_count(void);
  * Replaces: nothing in the reference (there the Scene is used in place); called once after main.cpp:76. */
 int trt_scene_create(const trt_scene_desc *desc, int device, trt_scene **out);
 void trt_scene_destroy(trt_scene *scene);
+
+/* trt_scene_create with the acceleration layouts kept in a file (since v201): when `layout_cache_path` holds the layouts
+ * of exactly this description — the file is keyed by a hash of every array and count the layouts are built from and of
+ * the environment switches that shape them, and carries a checksum — they are read instead of built (the build is most
+ * of trt_scene_create's host time on large scenes: 17 s of it at 10 M triangles).  Otherwise they are built as usual and
+ * the file is (re)written; a missing, stale, foreign, truncated or corrupt file is never an error, and neither is a file
+ * that cannot be written.  *from_cache (may be NULL) tells which happened.  The scene is the same either way.
+ * Replaces: nothing in the reference (it rebuilds its tree on every run, main.cpp:76). */
+int trt_scene_create_cached(const trt_scene_desc *desc, int device, const char *layout_cache_path, int32_t *from_cache,
+                            trt_scene **out);
 
 /* A copy of `scene` on another device, made from the device-resident arrays (device-to-device copies; the layouts
  * are not rebuilt on the host): how the scene is replicated for trt_render_multi ("BVH build: host, once,
@@ -305,6 +315,9 @@ typedef struct trt_layout_view {
 } trt_layout_view;
 typedef struct trt_layout trt_layout;
 int trt_layout_build(const trt_scene_desc *desc, trt_layout **out, trt_layout_view *view);
+/* the same through the layout cache of trt_scene_create_cached (host only: what the cache tests use) */
+int trt_layout_build_cached(const trt_scene_desc *desc, const char *layout_cache_path, int32_t *from_cache, trt_layout **out,
+                            trt_layout_view *view);
 void trt_layout_free(trt_layout *layout);
 
 int trt_get_stats(trt_scene *scene, trt_stats *out);

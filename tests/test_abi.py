@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert decl == set(api.EXPORTS), decl ^ set(api.EXPORTS)
     for s in decl:
         assert hasattr(lib, s), s
-    assert lib.trt_version() == 200
+    assert lib.trt_version() == 201
 
 
 def test_sm100a_sass_is_embedded():

@@ -220,3 +220,28 @@ def test_trace_closest_multi_shards_by_ray_index(host_scenes, oracle_scenes, dev
     finally:
         for d in reps:
             d.close()
+
+
+def test_scene_created_from_the_layout_cache_is_the_same_scene(host_scenes, device_scenes, tmp_path):
+    """trt_scene_create_cached: the first call builds the layouts and writes the file, the second reads it; ids, distance
+    bits and the frame are those of the scene that trt_scene_create builds."""
+    import tinyraytracing_b200 as trt
+
+    host, plain = host_scenes["staircase"], device_scenes["staircase"]
+    path = str(tmp_path / "staircase.layout")
+    rng = np.random.default_rng(5)
+    lo, hi = host.root_box()
+    rays = np.concatenate([rng.uniform(lo, hi, (40000, 3)), rng.normal(size=(40000, 3))], 1).astype(np.float32)
+    ref_ids, ref_t = plain.trace_closest(rays)
+    ref_img = plain.render(3, seed=8)
+    assert (ref_ids >= 0).mean() > 0.3
+    for expect_hit in (False, True):
+        dev = trt.DeviceScene(host, 0, layout_cache=path)
+        try:
+            assert dev.layout_from_cache == expect_hit
+            ids, t = dev.trace_closest(rays)
+            assert np.array_equal(ids, ref_ids) and np.array_equal(t.view(np.uint32), ref_t.view(np.uint32))
+            assert np.array_equal(dev.render(3, seed=8), ref_img)
+            assert dev.stats()["accel_nodes"] == plain.stats()["accel_nodes"]
+        finally:
+            dev.close()

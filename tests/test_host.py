@@ -326,3 +326,70 @@ def test_layout_with_interpenetrating_lights(seed):
     served = ids != -2
     assert served.mean() > 0.99
     assert np.array_equal(ids[served], oid[served]) and np.array_equal(t[served].view(np.uint32), ot[served].view(np.uint32))
+
+
+# ---- layout cache (trt_layout_build_cached / trt_scene_create_cached, csrc/layout_cache.cu) ----------------------------
+def _view_arrays(view):
+    """Every array of a trt_layout_view as bytes (+ its scalar fields): what 'the same layouts' means."""
+    import ctypes as C
+
+    def raw(ptr, n_bytes):
+        return C.string_at(ptr, n_bytes) if n_bytes else b""
+
+    nf, nl, ni, nw = view.n_fast_tris, view.n_ref_leaves, view.n_ref_inner, view.n_wide_nodes
+    return (
+        (nw, view.wide_root, nf, nl, ni, view.check_leaf_box, view.strict_origin_limit, view.miss_key),
+        raw(view.wide_nodes, nw * 128), raw(view.fast_geom, nf * 48), raw(view.fast_key, nf * 4), raw(view.fast_orig, nf * 4),
+        raw(view.fast_leaf, nf * 4), raw(view.ref_leaf_box, nl * 32), raw(view.ref_leaf_parent, nl * 4), raw(view.ref_nodes, ni * 64),
+    )
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_layout_cache_round_trip(name, host_scenes, tmp_path):
+    """Built once, read back: bit-identical layouts; the second call reads the file instead of building."""
+    host = host_scenes[name]
+    path = str(tmp_path / (name + ".layout"))
+    h0, v0 = host.layout_arrays()
+    h1, v1, hit1 = host.layout_arrays(layout_cache=path)  # no file yet: built and written
+    h2, v2, hit2 = host.layout_arrays(layout_cache=path)  # read back
+    try:
+        assert (hit1, hit2) == (False, True) and os.path.getsize(path) > 0
+        assert _view_arrays(v0) == _view_arrays(v1) == _view_arrays(v2)
+    finally:
+        for h in (h0, h1, h2):
+            host.free_layout(h)
+
+
+def test_layout_cache_rejects_what_is_not_its_own(host_scenes, tmp_path, monkeypatch):
+    """A stale, foreign, truncated or corrupt file is never an error and never used: the layouts are rebuilt and the file is
+    rewritten.  'Stale' includes another scene and another setting of a switch that shapes the layout."""
+    a, b = host_scenes["veach-mis"], host_scenes["back"]
+    path = str(tmp_path / "x.layout")
+
+    def build(host):
+        h, v, hit = host.layout_arrays(layout_cache=path)
+        arrays = _view_arrays(v)
+        host.free_layout(h)
+        return arrays, hit
+
+    ref_a, hit = build(a)
+    assert not hit and build(a) == (ref_a, True)
+    # another scene under the same path: rebuilt for that scene, file now holds scene b
+    ref_b, hit = build(b)
+    assert not hit and ref_b != ref_a and build(b) == (ref_b, True)
+    assert build(a) == (ref_a, False)
+    # a switch that shapes the layout is part of the key
+    monkeypatch.setenv("TRT_FAST_LEAF", "4")
+    leaf4, hit = build(a)
+    assert not hit and leaf4 != ref_a
+    monkeypatch.delenv("TRT_FAST_LEAF")
+    assert build(a) == (ref_a, False) and build(a) == (ref_a, True)
+    good = open(path, "rb").read()
+    for damage in (good[: len(good) // 2], good + b"\0", good[:100] + bytes([good[100] ^ 1]) + good[101:], b"", b"TRTLAYOT" + b"\0" * 64):
+        open(path, "wb").write(damage)
+        assert build(a) == (ref_a, False), len(damage)
+        assert open(path, "rb").read() == good  # rewritten
+    # an unwritable cache path costs nothing but the next build
+    h, v, hit = a.layout_arrays(layout_cache=str(tmp_path / "no_such_dir" / "x.layout"))
+    assert not hit and _view_arrays(v) == ref_a
+    a.free_layout(h)

@@ -83,7 +83,7 @@ class LayoutView(C.Structure):
 
 
 # every symbol include/trt.h and include/trt_host.h declare (tests check the library exports all of them)
-EXPORTS = ["trt_device_count", "trt_scene_create", "trt_scene_replicate", "trt_scene_destroy", "trt_host_alloc", "trt_host_free",
+EXPORTS = ["trt_device_count", "trt_scene_create", "trt_scene_create_cached", "trt_layout_build_cached", "trt_scene_replicate", "trt_scene_destroy", "trt_host_alloc", "trt_host_free",
            "trt_trace_closest", "trt_trace_closest_multi", "trt_trace_closest_async", "trt_trace_counters", "trt_hit_attributes", "trt_render",
            "trt_render_accumulate", "trt_resolve", "trt_render_multi", "trt_shade", "trt_accum_create", "trt_accum_destroy",
            "trt_accum_save", "trt_accum_load", "trt_layout_check", "trt_layout_build", "trt_layout_free", "trt_get_stats", "trt_reset_stats", "trt_last_error",
@@ -127,6 +127,8 @@ def load_library():
     L.trt_render.argtypes = [vp, C.POINTER(RenderParams), vp]
     L.trt_layout_check.argtypes = [C.POINTER(SceneDesc), C.POINTER(LayoutReport)]
     L.trt_layout_build.argtypes = [C.POINTER(SceneDesc), C.POINTER(vp), C.POINTER(LayoutView)]
+    L.trt_layout_build_cached.argtypes = [C.POINTER(SceneDesc), C.c_char_p, C.POINTER(C.c_int32), C.POINTER(vp), C.POINTER(LayoutView)]
+    L.trt_scene_create_cached.argtypes = [C.POINTER(SceneDesc), C.c_int, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(vp)]
     L.trt_layout_free.argtypes = [vp]
     L.trt_layout_free.restype = None
     L.trt_render_accumulate.argtypes = [vp, C.POINTER(RenderParams), vp, vp]
@@ -203,12 +205,19 @@ class HostScene:
         _check(load_library().trt_host_scene_load_cache(path.encode(), C.byref(h)), "trt_host_scene_load_cache")
         return cls(h)
 
-    def layout_arrays(self):
+    def layout_arrays(self, layout_cache=None):
         """(handle, LayoutView): the GPU layouts of this scene as plain host arrays (trt_layout_build); release the
-        handle with free_layout().  Inspection / test tooling — the device path never reads it."""
+        handle with free_layout().  Inspection / test tooling — the device path never reads it.
+        With layout_cache=<path> the layouts go through the layout cache (trt_layout_build_cached) and the call returns
+        (handle, view, from_cache)."""
         h, view = C.c_void_p(), LayoutView()
-        _check(self.lib.trt_layout_build(C.byref(self.desc), C.byref(h), C.byref(view)), "trt_layout_build")
-        return h, view
+        if layout_cache is None:
+            _check(self.lib.trt_layout_build(C.byref(self.desc), C.byref(h), C.byref(view)), "trt_layout_build")
+            return h, view
+        hit = C.c_int32(0)
+        _check(self.lib.trt_layout_build_cached(C.byref(self.desc), os.fsencode(layout_cache), C.byref(hit), C.byref(h), C.byref(view)),
+               "trt_layout_build_cached")
+        return h, view, bool(hit.value)
 
     def free_layout(self, handle):
         self.lib.trt_layout_free(handle)
@@ -347,11 +356,17 @@ def render_multi(devs, spp, seed=0, max_depth=0, flags=0, batch_paths=0, want_rg
 class DeviceScene:
     """Device-resident scene: the GPU hot path (closest hit, render). Needs an sm_100 GPU."""
 
-    def __init__(self, host_scene, device=0, _replica_of=None):
+    def __init__(self, host_scene, device=0, _replica_of=None, layout_cache=None):
         self.lib = load_library()
         self.host = host_scene
         self.h = C.c_void_p()
-        if _replica_of is None:
+        self.layout_from_cache = False  # layout_cache=<path>: trt_scene_create_cached (layouts read from / written to the file)
+        if _replica_of is None and layout_cache is not None:
+            hit = C.c_int32(0)
+            _check(self.lib.trt_scene_create_cached(C.byref(host_scene.desc), device, os.fsencode(layout_cache), C.byref(hit),
+                                                    C.byref(self.h)), "trt_scene_create_cached")
+            self.layout_from_cache = bool(hit.value)
+        elif _replica_of is None:
             _check(self.lib.trt_scene_create(C.byref(host_scene.desc), device, C.byref(self.h)), "trt_scene_create")
         else:
             _check(self.lib.trt_scene_replicate(_replica_of.h, device, C.byref(self.h)), "trt_scene_replicate")

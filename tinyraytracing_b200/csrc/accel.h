@@ -163,4 +163,10 @@ std::string checkLayout(const trt_scene_desc &desc, const AccelBuild &ab, trt_la
 // Builds the 4-wide fast layout over the reference leaves into `out` (after buildAccel). A non-empty return
 // means the layout is unavailable for this scene (the reference-topology kernels are used instead).
 std::string buildWide(const trt_scene_desc &desc, AccelBuild &out);
+
+// ---- layout cache (layout_cache.cu): the whole AccelBuild in one file, keyed by a hash of what it was built from ----
+uint64_t layoutKey(const trt_scene_desc &desc);
+std::string saveLayout(const AccelBuild &ab, bool use_wide, uint64_t key, const char *path); // "" or why not
+// true: `path` held the layouts for this key, `ab` / `use_wide` are filled; false: `why` says what was wrong with the file
+bool loadLayout(const char *path, uint64_t key, AccelBuild &ab, bool &use_wide, std::string &why);
 } // namespace trt

@@ -232,17 +232,54 @@ void trt_host_free(void *p)
         cudaFreeHost(p);
 }
 
-static int sceneCreate(const trt_scene_desc *desc, int device, trt_scene **out);
+static int sceneCreate(const trt_scene_desc *desc, int device, const char *layout_cache, int32_t *from_cache, trt_scene **out);
 
 int trt_scene_create(const trt_scene_desc *desc, int device, trt_scene **out)
 {
     if (!desc || !out)
         return fail(TRT_ERR_INVALID, "trt_scene_create: null argument");
     *out = nullptr;
-    return guarded("trt_scene_create", [&] { return sceneCreate(desc, device, out); });
+    return guarded("trt_scene_create", [&] { return sceneCreate(desc, device, nullptr, nullptr, out); });
 }
 
-static int sceneCreate(const trt_scene_desc *desc, int device, trt_scene **out)
+int trt_scene_create_cached(const trt_scene_desc *desc, int device, const char *layout_cache_path, int32_t *from_cache,
+                            trt_scene **out)
+{
+    if (!desc || !out || !layout_cache_path)
+        return fail(TRT_ERR_INVALID, "trt_scene_create_cached: null argument");
+    *out = nullptr;
+    if (from_cache)
+        *from_cache = 0;
+    return guarded("trt_scene_create_cached", [&] { return sceneCreate(desc, device, layout_cache_path, from_cache, out); });
+}
+
+// The layouts of a (validated) description: from the cache file when it holds them, built (and written there) otherwise.
+// use_wide = 0: the scene keeps the reference-topology kernels (single leaf / too deep / empty).  "" or an error text.
+static std::string makeLayouts(const trt_scene_desc &desc, const char *layout_cache, AccelBuild &ab, bool &use_wide,
+                               bool &from_cache)
+{
+    from_cache = false;
+    uint64_t key = 0;
+    if (layout_cache)
+    {
+        key = layoutKey(desc);
+        std::string why;
+        if (loadLayout(layout_cache, key, ab, use_wide, why))
+        {
+            from_cache = true;
+            return "";
+        }
+    }
+    const std::string err = buildAccel(desc, ab);
+    if (!err.empty())
+        return err;
+    use_wide = buildWide(desc, ab).empty(); // an error text here only means "this scene keeps the reference-topology kernels"
+    if (layout_cache)
+        saveLayout(ab, use_wide, key, layout_cache); // best effort: a cache that cannot be written costs the next build, nothing else
+    return "";
+}
+
+static int sceneCreate(const trt_scene_desc *desc, int device, const char *layout_cache, int32_t *from_cache_out, trt_scene **out)
 {
     const std::string bad = validateDesc(*desc);
     if (!bad.empty())
@@ -257,9 +294,12 @@ static int sceneCreate(const trt_scene_desc *desc, int device, trt_scene **out)
         return fail(TRT_ERR_NO_DEVICE, "device is not an sm_100 (B200) GPU: this library ships sm_100a code only");
 
     AccelBuild ab;
-    std::string err = buildAccel(*desc, ab);
+    bool use_wide = false, from_cache = false;
+    std::string err = makeLayouts(*desc, layout_cache, ab, use_wide, from_cache);
     if (!err.empty())
         return fail(TRT_ERR_INVALID, "trt_scene_create: " + err);
+    if (from_cache_out)
+        *from_cache_out = from_cache ? 1 : 0;
     if (ab.ref_depth >= TRT_REF_STACK_LIMIT)
         return fail(TRT_ERR_LIMIT, "reference tree deeper than the traversal stack (" +
                                        std::to_string(ab.ref_depth) + " >= " + std::to_string(TRT_REF_STACK_LIMIT) + ")");
@@ -289,8 +329,7 @@ static int sceneCreate(const trt_scene_desc *desc, int device, trt_scene **out)
     v.miss_rank = ab.miss_rank;
     v.root_link = ab.root_link;
     v.n_tris = desc->n_tris;
-    const std::string wide_err = buildWide(*desc, ab);
-    v.use_wide = wide_err.empty() ? 1 : 0;
+    v.use_wide = use_wide ? 1 : 0;
     v.wide_root = ab.wide_root;
     if ((rc = upload(s.get(), ab.wide_nodes.data(), ab.wide_nodes.size(), &v.wide_nodes)) ||
         (rc = upload(s.get(), ab.fast_geom.data(), ab.fast_geom.size(), &v.fast_geom)) ||
@@ -727,7 +766,26 @@ struct trt_layout
     trt::AccelBuild ab;
 };
 
+static int layoutBuild(const trt_scene_desc *desc, const char *layout_cache, int32_t *from_cache_out, trt_layout **out,
+                       trt_layout_view *view);
+
 int trt_layout_build(const trt_scene_desc *desc, trt_layout **out, trt_layout_view *view)
+{
+    return layoutBuild(desc, nullptr, nullptr, out, view);
+}
+
+int trt_layout_build_cached(const trt_scene_desc *desc, const char *layout_cache_path, int32_t *from_cache, trt_layout **out,
+                            trt_layout_view *view)
+{
+    if (!layout_cache_path)
+        return fail(TRT_ERR_INVALID, "trt_layout_build_cached: null argument");
+    if (from_cache)
+        *from_cache = 0;
+    return layoutBuild(desc, layout_cache_path, from_cache, out, view);
+}
+
+static int layoutBuild(const trt_scene_desc *desc, const char *layout_cache, int32_t *from_cache_out, trt_layout **out,
+                       trt_layout_view *view)
 {
     if (!desc || !out || !view)
         return fail(TRT_ERR_INVALID, "trt_layout_build: null argument");
@@ -737,14 +795,16 @@ int trt_layout_build(const trt_scene_desc *desc, trt_layout **out, trt_layout_vi
         return fail(TRT_ERR_INVALID, "trt_layout_build: " + bad);
     std::unique_ptr<trt_layout> l(new trt_layout());
     AccelBuild &ab = l->ab;
-    const std::string err = buildAccel(*desc, ab);
+    bool use_wide = false, from_cache = false;
+    const std::string err = makeLayouts(*desc, layout_cache, ab, use_wide, from_cache);
     if (!err.empty())
         return fail(TRT_ERR_INVALID, "trt_layout_build: " + err);
-    const std::string wide_err = buildWide(*desc, ab);
+    if (from_cache_out)
+        *from_cache_out = from_cache ? 1 : 0;
     static_assert(sizeof(WideNode) == 128 && sizeof(TriGeom) == 48 && sizeof(RefNode) == 64, "layout records");
     std::memset(view, 0, sizeof *view);
     view->n_wide_nodes = (int32_t)ab.wide_nodes.size();
-    view->wide_root = wide_err.empty() ? ab.wide_root : TRT_LINK_EMPTY;
+    view->wide_root = use_wide ? ab.wide_root : TRT_LINK_EMPTY;
     view->n_fast_tris = (int32_t)ab.fast_orig.size();
     view->n_ref_leaves = (int32_t)ab.ref_leaf_parent.size();
     view->n_ref_inner = (int32_t)ab.ref_nodes.size();

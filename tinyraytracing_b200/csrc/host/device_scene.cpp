@@ -147,10 +147,12 @@ std::unique_ptr<SceneArrays> makeSceneArrays(Scene &scene, const BVHNode *root)
     return a;
 }
 
-DeviceScene::DeviceScene(Scene &scene, BVHNode *root, int device) : scene_(&scene)
+DeviceScene::DeviceScene(Scene &scene, BVHNode *root, int device, const char *layout_cache) : scene_(&scene)
 {
     auto arrays = makeSceneArrays(scene, root);
-    if (trt_scene_create(&arrays->desc, device, &h_) != TRT_OK)
+    const int rc = layout_cache ? trt_scene_create_cached(&arrays->desc, device, layout_cache, nullptr, &h_)
+                                : trt_scene_create(&arrays->desc, device, &h_);
+    if (rc != TRT_OK)
         throw std::runtime_error(std::string("trt_scene_create: ") + trt_last_error());
 }
 

@@ -86,7 +86,7 @@ int main()
             devices.push_back(device);
         std::vector<std::unique_ptr<DeviceScene>> devs;
         for (int d : devices) // the scene is replicated on every GPU: built and uploaded once, then copied device to device
-            devs.emplace_back(devs.empty() ? new DeviceScene(scene, root, d) : new DeviceScene(*devs[0], d, true));
+            devs.emplace_back(devs.empty() ? new DeviceScene(scene, root, d, std::getenv("TRT_LAYOUT_CACHE")) : new DeviceScene(*devs[0], d, true));
         DeviceScene &dev = *devs[0];
         const char *ckpt = std::getenv("TRT_CHECKPOINT");
         if (devs.size() > 1)

@@ -144,7 +144,9 @@ int nodeCountBVH(const BVHNode *root);
 class DeviceScene
 {
 public:
-    DeviceScene(Scene &scene, BVHNode *root, int device = 0);
+    // layout_cache: a file for the acceleration layouts (trt_scene_create_cached: read when it holds this scene's, else
+    // built and written there); nullptr = build every time
+    DeviceScene(Scene &scene, BVHNode *root, int device = 0, const char *layout_cache = nullptr);
     // replica of `src` on another GPU (trt_scene_replicate: device-to-device copy, the layouts are not rebuilt)
     DeviceScene(const DeviceScene &src, int device, bool replicate);
     ~DeviceScene();

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <string>
 #include <type_traits>
+#include <unistd.h>
 
 namespace trt
 {
@@ -156,7 +157,9 @@ std::string saveLayout(const AccelBuild &ab_in, bool use_wide, uint64_t key, con
     h.version = kFormatVersion, h.use_wide = use_wide ? 1u : 0u, h.key = key;
     h.payload_bytes = w.buf.size();
     h.checksum = fnv(w.buf.data(), w.buf.size(), 1469598103934665603ull);
-    const std::string tmp = std::string(path) + ".tmp";
+    // (the process id in the name: several processes may create the same scene with the same cache path at once — each
+    // writes its own file and the renames are atomic, so the survivor is one complete file)
+    const std::string tmp = std::string(path) + ".tmp." + std::to_string((long long)getpid());
     FILE *f = std::fopen(tmp.c_str(), "wb");
     if (!f)
         return "cannot open " + tmp;

@@ -107,6 +107,8 @@ uint64_t layoutKey(const trt_scene_desc &d)
 {
     uint64_t h = 1469598103934665603ull;
     h = fnvValue(kFormatVersion, h);
+    const uint32_t library = TRT_VERSION; // a layout written by another version of the builders is rebuilt, not trusted
+    h = fnvValue(library, h);
     const uint32_t sizes[4] = {(uint32_t)sizeof(RefNode), (uint32_t)sizeof(WideNode), (uint32_t)sizeof(TriGeom), (uint32_t)TRT_WIDE_STACK};
     h = fnv(sizes, sizeof sizes, h);
     // the switches that shape the layout
